@@ -1,0 +1,670 @@
+// csrc/capi.cu -- the C ABI declared in include/dfb200.h: handle lifetime, device layout, the step.
+// Mirrors DIGITAL_FILTER's constructor (df.cpp:4-66) and filter(dt) (df.cpp:449-468).
+// There is no CPU fallback: without an sm_100 device dfb_create fails with DFB_ERR_CUDA.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+#include "dfb200.h"
+#include "plan.hpp"
+#include "noise.cuh"
+#include "device.cuh"
+#include "kernels.hpp"
+
+using namespace dfb;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (expr);                                                                   \
+        if (e__ != cudaSuccess)                                                                     \
+            throw Error{DFB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)};         \
+    } while (0)
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+struct NoiseHost {            // one logical array of the noise contract
+    int field, kind;
+    uint64_t inc, state0, npairs;
+    int n_seg;
+    void *d_jump = nullptr, *d_q0 = nullptr, *d_np = nullptr;
+};
+
+}  // namespace
+
+struct dfb_filter_s {
+    Plan plan;
+    int device = 0;
+    int noise_mode = DFB_NOISE_GENERATE;
+    int kernel_variant = 0;
+    bool tuned = false;
+    uint64_t seed = 0;
+    int plane_id = 0;
+    int64_t step = 0;                 // steps completed (the constructor's first step counts as one)
+    bool injected[3] = {false, false, false};
+    cudaStream_t stream = nullptr;
+    std::vector<void*> allocs;
+    PlaneDev D{};
+    // tuned y-sweep
+    YMaps maps{};
+    YParams yp{};
+    int n_items = 0;
+    // tuned z-sweep
+    ZParams zp{};
+    // noise
+    std::vector<NoiseHost> noise;
+    NoiseParams np{};
+    // timing
+    bool timing = false;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    float last_ms[4] = {0, 0, 0, 0};
+
+    template <class T>
+    T* dalloc(size_t n, bool zero = true) {
+        void* p = nullptr;
+        CUDA_TRY(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+        allocs.push_back(p);
+        if (zero) CUDA_TRY(cudaMemsetAsync(p, 0, std::max<size_t>(n, 1) * sizeof(T), stream));
+        return static_cast<T*>(p);
+    }
+    template <class T>
+    T* upload(const std::vector<T>& v) {
+        T* p = dalloc<T>(v.size(), false);
+        if (!v.empty()) CUDA_TRY(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, stream));
+        return p;
+    }
+    ~dfb_filter_s() {
+        cudaSetDevice(device);
+        if (stream) cudaStreamSynchronize(stream);
+        for (void* p : allocs) cudaFree(p);
+        for (auto& e : ev) if (e) cudaEventDestroy(e);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+        if (q != cudaDriverEntryPointSuccess || !p) throw Error{DFB_ERR_CUDA, "cuTensorMapEncodeTiled not available"};
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+void build_device(dfb_filter_s& H) {
+    const Plan& P = H.plan;
+    PlaneDev& D = H.D;
+    const int Ny = P.Ny, W = P.Nz(), NzG = P.NzG;
+    D.Ny = Ny; D.W = W; D.NzG = NzG; D.k0 = P.k0;
+    H.tuned = (H.kernel_variant == 0) && P.f[0].row_uniform && P.f[1].row_uniform && P.f[2].row_uniform;
+
+    // ---- per-row epilogue constants, reference expressions (df.cpp:425-438, 474) ----
+    std::vector<double> rowc((size_t)Ny * ROWC, 0.0);
+    const double* R11 = P.rows.data(); const double* R21 = R11 + Ny; const double* R22 = R21 + Ny; const double* R33 = R22 + Ny;
+    const double* Us = R33 + Ny; const double* Ts = Us + Ny; const double* rhos = Ts + Ny; const double* Ms = rhos + Ny;
+    for (int j = 0; j < Ny; ++j) {
+        double b = (R11[j] < 1e-10) ? 0.0 : R21[j] / std::sqrt(R11[j]);
+        double* rc = &rowc[(size_t)j * ROWC];
+        rc[0] = std::sqrt(R11[j]);
+        rc[1] = b;
+        rc[2] = std::sqrt(R22[j] - b * b);
+        rc[3] = std::sqrt(R33[j]);
+        rc[4] = -0.5 * (1.4 - 1) * Ms[j] * Ms[j] / Us[j];
+        rc[5] = Ts[j];
+        rc[6] = rhos[j];
+    }
+    D.rowc = H.upload(rowc);
+    D.coef_ptr = H.upload(P.coef.ptr);
+    D.coef_vals = H.upload(P.coef.vals);
+    D.T_fluc = H.dalloc<double>((size_t)Ny * W);
+    D.rho_fluc = H.dalloc<double>((size_t)Ny * W);
+
+    int maxNz = 0;
+    for (int f = 0; f < 3; ++f) {
+        const FieldPlan& FP = P.f[f];
+        FieldDev& F = D.f[f];
+        F.Ny_max = FP.Ny_max; F.Nz_max = FP.Nz_max;
+        maxNz = std::max(maxNz, FP.Nz_max);
+        F.rows_y = Ny + 2 * FP.Ny_max;
+        F.xk0 = std::max(0, P.k0 - FP.Nz_max);
+        const int xk1 = std::min(NzG, P.k1 + FP.Nz_max);
+        F.We = xk1 - F.xk0;
+        F.pitch_y = round_up(F.We, 16);
+        F.zoff = (16 - FP.Nz_max % 16) % 16;
+        F.pitch_z = round_up(F.zoff + W + 2 * FP.Nz_max, 16) + 16;
+        F.yshift = F.xk0 - P.k0 + FP.Nz_max;
+        F.r_ys = H.dalloc<double>((size_t)F.rows_y * F.pitch_y);
+        F.r_zs = H.dalloc<double>((size_t)Ny * F.pitch_z);
+        F.filt_old = H.dalloc<double>((size_t)Ny * W);
+        F.fluc = H.dalloc<double>((size_t)Ny * W);
+        F.Ny_row = H.upload(FP.N_y_row);
+        F.Nz_row = H.upload(FP.N_z_row);
+        F.Ny_cell = FP.row_uniform ? nullptr : H.upload(FP.N_y);
+        F.Nz_cell = FP.row_uniform ? nullptr : H.upload(FP.N_z);
+    }
+
+    // ---- tuned y-sweep: row groups, dense band matrices, work items, TMA maps ----
+    if (H.tuned) {
+        const int RC = ysweep_rc();
+        std::vector<YGroup> groups;
+        std::vector<double> cmat;
+        for (int f = 0; f < 3; ++f) {
+            const FieldPlan& FP = P.f[f];
+            for (int j0 = 0; j0 < Ny; j0 += YJ) {
+                YGroup g{};
+                g.field = f; g.j0 = j0; g.nrows = std::min(YJ, Ny - j0);
+                g.Nmax = 0;
+                for (int jj = 0; jj < g.nrows; ++jj) g.Nmax = std::max(g.Nmax, FP.N_y_row[j0 + jj]);
+                g.row0 = j0 + FP.Ny_max - g.Nmax;
+                const int T = g.nrows + 2 * g.Nmax;
+                g.nchunks = (T + RC - 1) / RC;
+                g.cmat_off = (long long)cmat.size();
+                cmat.resize(cmat.size() + (size_t)g.nchunks * RC * YJ, 0.0);
+                double* cm = cmat.data() + g.cmat_off;
+                for (int jj = 0; jj < g.nrows; ++jj) {
+                    const int N = FP.N_y_row[j0 + jj];
+                    const double* b = P.coef.centre(N);
+                    for (int i = -N; i <= N; ++i) cm[(size_t)(g.Nmax + jj + i) * YJ + jj] = b[i];
+                }
+                groups.push_back(g);
+            }
+        }
+        std::vector<YItem> items;
+        for (int gi = 0; gi < (int)groups.size(); ++gi)
+            for (int c0 = 0; c0 < D.f[groups[gi].field].We; c0 += Y_TK) items.push_back(YItem{gi, c0});
+        std::stable_sort(items.begin(), items.end(), [&](const YItem& a, const YItem& b) {
+            return groups[a.group].nchunks > groups[b.group].nchunks;   // longest first
+        });
+        H.yp.groups = H.upload(groups);
+        H.yp.items = H.upload(items);
+        H.yp.cmat = H.upload(cmat);
+        H.yp.D = D;
+        H.n_items = (int)items.size();
+        for (int f = 0; f < 3; ++f) {
+            const FieldDev& F = D.f[f];
+            cuuint64_t dims[2] = {(cuuint64_t)F.We, (cuuint64_t)F.rows_y};
+            cuuint64_t strides[1] = {(cuuint64_t)F.pitch_y * sizeof(double)};
+            cuuint32_t box[2] = {128u, (cuuint32_t)RC};
+            cuuint32_t estr[2] = {1u, 1u};
+            CUresult r = encode_tiled()(&H.maps.m[f], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, F.r_ys, dims, strides, box, estr,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) throw Error{DFB_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")"};
+        }
+        CUDA_TRY(ysweep_prepare());
+        H.zp.D = D;
+        H.zp.max_len = Z_TK + 8 + round_up(2 * maxNz, 8);
+        H.zp.max_coef = 2 * maxNz + 32;
+        CUDA_TRY(zsweep_prepare(zsweep_smem_bytes(H.zp.max_len, H.zp.max_coef)));
+    }
+
+    // ---- noise tables (include/dfb_rng_spec.h) ----
+    int max_np = 1;
+    for (int f = 0; f < 3; ++f) {
+        const FieldDev& F = D.f[f];
+        for (int kind = 0; kind < 2; ++kind) {
+            NoiseHost A{};
+            A.field = f; A.kind = kind;
+            const uint64_t stream = (uint64_t)(((int64_t)H.plane_id * 3 + f) * 2 + kind);
+            A.inc = (stream << 1) | 1u;
+            A.state0 = pcg_lcg(H.seed + A.inc, A.inc);
+            std::vector<Jump> jumps;
+            std::vector<long long> q0;
+            std::vector<int> npv;
+            if (kind == 0) {
+                A.npairs = ((uint64_t)F.rows_y * (uint64_t)NzG + 1u) / 2u;
+                for (int r = 0; r < F.rows_y; ++r) {
+                    const long long ea = (long long)r * NzG + F.xk0, eb = ea + F.We - 1;
+                    const long long qa = ea >> 1, qb = eb >> 1;
+                    q0.push_back(qa); npv.push_back((int)(qb - qa + 1));
+                    jumps.push_back(pcg_jump(4u * (uint64_t)qa, 1u));
+                }
+            } else {
+                const int M = F.Nz_max;
+                A.npairs = (uint64_t)Ny * (uint64_t)M;
+                const bool touches = (P.k0 - M < 0) || (P.k1 + M > NzG);
+                if (M > 0 && touches)
+                    for (int j = 0; j < Ny; ++j) {
+                        q0.push_back((long long)j * M); npv.push_back(M);
+                        jumps.push_back(pcg_jump(4u * (uint64_t)j * (uint64_t)M, 1u));
+                    }
+            }
+            A.n_seg = (int)q0.size();
+            for (int v : npv) max_np = std::max(max_np, v);
+            if (A.n_seg) {
+                A.d_jump = H.upload(jumps); A.d_q0 = H.upload(q0); A.d_np = H.upload(npv);
+            }
+            H.noise.push_back(A);
+        }
+    }
+    std::vector<Jump> slot(max_np);
+    for (int t = 0; t < max_np; ++t) slot[t] = pcg_jump(4u * (uint64_t)t, 1u);
+    H.np.slot_jump = H.upload(slot);
+    H.np.max_np = max_np;
+    H.np.chunks = (max_np + 127) / 128;
+    CUDA_TRY(cudaStreamSynchronize(H.stream));
+}
+
+void fill_noise_params(dfb_filter_s& H, int64_t step) {
+    int n = 0;
+    for (const NoiseHost& A : H.noise) {
+        if (!A.n_seg) continue;
+        NoiseArray& a = H.np.a[n++];
+        const Jump j = pcg_jump(4u * ((uint64_t)step * A.npairs), A.inc);
+        a.state = j.A * A.state0 + j.C;
+        a.inc = A.inc;
+        a.seg_jump = A.d_jump; a.seg_q0 = static_cast<const long long*>(A.d_q0); a.seg_np = static_cast<const int*>(A.d_np);
+        a.n_seg = A.n_seg; a.kind = A.kind; a.field = A.field;
+    }
+    H.np.n_arrays = n;
+}
+
+void run_step(dfb_filter_s& H, double dt, bool first) {
+    CUDA_TRY(cudaSetDevice(H.device));
+    if (H.timing) CUDA_TRY(cudaEventRecord(H.ev[0], H.stream));
+    if (H.noise_mode == DFB_NOISE_GENERATE) {
+        fill_noise_params(H, H.step);
+        CUDA_TRY(launch_noise(H.np, H.D, H.stream));
+    } else if (!(H.injected[0] && H.injected[1] && H.injected[2])) {
+        throw Error{DFB_ERR_STATE, "noise_mode = inject: dfb_set_noise must be called for u, v and w before every step"};
+    }
+    if (H.timing) CUDA_TRY(cudaEventRecord(H.ev[1], H.stream));
+    if (H.tuned) CUDA_TRY(launch_ysweep_tma(H.maps, H.yp, H.n_items, H.stream));
+    else CUDA_TRY(launch_ysweep_simple(H.D, H.stream));
+    if (H.timing) CUDA_TRY(cudaEventRecord(H.ev[2], H.stream));
+    StepConsts S{};
+    S.first_step = first ? 1 : 0;
+    for (int f = 0; f < 3; ++f) {
+        const double pi = 3.141592654;                             // df.cpp:411
+        const double alpha = std::exp(-pi * dt / H.plan.f[f].Lt);  // df.cpp:412
+        S.sa[f] = std::sqrt(alpha);                                // df.cpp:415
+        S.sb[f] = std::sqrt(1.0 - alpha);
+    }
+    if (H.tuned) { H.zp.S = S; CUDA_TRY(launch_zsweep_tuned(H.zp, H.stream)); }
+    else CUDA_TRY(launch_zsweep_simple(H.D, S, H.stream));
+    if (H.timing) CUDA_TRY(cudaEventRecord(H.ev[3], H.stream));
+    H.step += 1;
+    H.injected[0] = H.injected[1] = H.injected[2] = false;
+    if (H.timing) {
+        CUDA_TRY(cudaEventSynchronize(H.ev[3]));
+        for (int s = 0; s < 3; ++s) CUDA_TRY(cudaEventElapsedTime(&H.last_ms[s], H.ev[s], H.ev[s + 1]));
+        CUDA_TRY(cudaEventElapsedTime(&H.last_ms[3], H.ev[0], H.ev[3]));
+    }
+}
+
+const double* field_ptr(const dfb_filter_s& H, int which) {
+    switch (which) {
+        case DFB_U_FLUC: return H.D.f[0].fluc;   case DFB_V_FLUC: return H.D.f[1].fluc;   case DFB_W_FLUC: return H.D.f[2].fluc;
+        case DFB_T_FLUC: return H.D.T_fluc;      case DFB_RHO_FLUC: return H.D.rho_fluc;
+        case DFB_U_FILT: return H.D.f[0].filt_old; case DFB_V_FILT: return H.D.f[1].filt_old; case DFB_W_FILT: return H.D.f[2].filt_old;
+    }
+    return nullptr;
+}
+
+template <class Fn>
+int guarded(Fn&& fn) {
+    try {
+        fn();
+        return DFB_OK;
+    } catch (const Error& e) {
+        return fail(e.code, e.msg);
+    } catch (const std::bad_alloc&) {
+        return fail(DFB_ERR_ARG, "host allocation failed");
+    } catch (const std::exception& e) {
+        return fail(DFB_ERR_ARG, e.what());
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int dfb_config_init(dfb_config* cfg) {
+    if (!cfg) return fail(DFB_ERR_ARG, "cfg is NULL");
+    std::memset(cfg, 0, sizeof(*cfg));
+    cfg->struct_bytes = (int)sizeof(dfb_config);
+    cfg->grid_file_len = cfg->vel_fluc_file_len = cfg->line_file_len = -1;
+    cfg->device = -1;
+    return DFB_OK;
+}
+
+int dfb_create(const dfb_config* cfg, dfb_handle* out) {
+    if (!cfg || !out) return fail(DFB_ERR_ARG, "cfg/out is NULL");
+    *out = nullptr;
+    if (cfg->struct_bytes != (int)sizeof(dfb_config))
+        return fail(DFB_ERR_ARG, "dfb_config.struct_bytes does not match this library (call dfb_config_init first)");
+    std::unique_ptr<dfb_filter_s> H(new dfb_filter_s());
+    int rc = guarded([&] {
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0)
+            throw Error{DFB_ERR_CUDA, std::string("no CUDA device (") + cudaGetErrorString(e) + "); this library has no CPU fallback"};
+        int dev = cfg->device;
+        if (dev < 0) CUDA_TRY(cudaGetDevice(&dev));
+        if (dev >= ndev) throw Error{DFB_ERR_ARG, "device ordinal out of range"};
+        cudaDeviceProp prop;
+        CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+        if (prop.major != 10)
+            throw Error{DFB_ERR_CUDA, std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                                          "; the kernels are built for sm_100a only and there is no fallback"};
+        H->device = dev;
+        CUDA_TRY(cudaSetDevice(dev));
+        if (cfg->noise_mode != DFB_NOISE_GENERATE && cfg->noise_mode != DFB_NOISE_INJECT) throw Error{DFB_ERR_ARG, "bad noise_mode"};
+        H->noise_mode = cfg->noise_mode;
+        H->kernel_variant = cfg->kernel_variant;
+        H->seed = cfg->seed;
+        H->plane_id = cfg->plane_id;
+        build_plan(*cfg, H->plan);
+        if (H->noise_mode == DFB_NOISE_INJECT && (H->plan.k0 != 0 || H->plan.k1 != H->plan.NzG))
+            throw Error{DFB_ERR_ARG, "noise injection is defined on the whole plane (k_begin = k_end = 0)"};
+        CUDA_TRY(cudaStreamCreateWithFlags(&H->stream, cudaStreamNonBlocking));
+        for (auto& e2 : H->ev) CUDA_TRY(cudaEventCreate(&e2));
+        build_device(*H);
+        // first step of the constructor, df.cpp:57-62 (generate mode only: in inject mode the
+        // caller owns the noise and runs it through dfb_first_step semantics via dfb_filter after
+        // dfb_set_noise; see dfb_set_state for a step counter of 0)
+        if (H->noise_mode == DFB_NOISE_GENERATE && !cfg->skip_first_step) {
+            run_step(*H, 0.0, true);
+            CUDA_TRY(cudaStreamSynchronize(H->stream));
+        }
+    });
+    if (rc != DFB_OK) return rc;
+    *out = H.release();
+    return DFB_OK;
+}
+
+int dfb_destroy(dfb_handle h) {
+    if (!h) return DFB_OK;
+    delete h;
+    return DFB_OK;
+}
+
+int dfb_dims(dfb_handle h, int* Ny, int* Nz) {
+    if (!h) return fail(DFB_ERR_ARG, "handle is NULL");
+    if (Ny) *Ny = h->plan.Ny;
+    if (Nz) *Nz = h->plan.Nz();
+    return DFB_OK;
+}
+
+int dfb_info(dfb_handle h, int what, int field, int64_t* out64) {
+    if (!h || !out64) return fail(DFB_ERR_ARG, "handle/out is NULL");
+    if (field < 0 || field > 2) return fail(DFB_ERR_ARG, "field must be 0..2");
+    switch (what) {
+        case 0: *out64 = h->plan.f[field].Ny_max; break;
+        case 1: *out64 = h->plan.f[field].Nz_max; break;
+        case 2: *out64 = h->step; break;
+        case 3: *out64 = h->tuned ? 1 : 0; break;
+        case 4: *out64 = h->plan.taps_per_step; break;
+        case 5: *out64 = h->plan.NzG; break;
+        default: return fail(DFB_ERR_ARG, "unknown info selector");
+    }
+    return DFB_OK;
+}
+
+int dfb_get_table(dfb_handle h, int which, int arg, double* dst, int cap) {
+    if (!h || !dst) return fail(DFB_ERR_ARG, "handle/dst is NULL");
+    const Plan& P = h->plan;
+    const double* src = nullptr;
+    int n = 0;
+    std::vector<double> tmp;
+    if (which >= 0 && which < 8) { src = P.rows.data() + (size_t)which * P.Ny; n = P.Ny; }
+    else if (which == 8) { src = P.yc_row.data(); n = P.Ny; }
+    else if (which == 9) { src = P.dy_row.data(); n = P.Ny; }
+    else if (which == 10) { tmp = {P.f[0].Lt, P.f[1].Lt, P.f[2].Lt}; src = tmp.data(); n = 3; }
+    else if (which == 11) {
+        if (arg < 0 || arg > P.coef.Nmax || P.coef.ptr[arg] < 0) return fail(DFB_ERR_ARG, "half-width not present in this plane");
+        src = P.coef.vals.data() + P.coef.ptr[arg]; n = 2 * arg + 1;
+    } else return fail(DFB_ERR_ARG, "unknown table selector");
+    if (cap < n) return fail(DFB_ERR_ARG, "dst too small");
+    std::memcpy(dst, src, sizeof(double) * n);
+    return DFB_OK;
+}
+
+int dfb_get_half_widths(dfb_handle h, int field, int dir, int* dst) {
+    if (!h || !dst || field < 0 || field > 2) return fail(DFB_ERR_ARG, "bad argument");
+    const Plan& P = h->plan;
+    const FieldPlan& F = P.f[field];
+    for (int j = 0; j < P.Ny; ++j)
+        for (int k = P.k0; k < P.k1; ++k) {
+            int v = F.row_uniform ? (dir ? F.N_z_row[j] : F.N_y_row[j])
+                                  : (dir ? F.N_z[(size_t)j * P.NzG + k] : F.N_y[(size_t)j * P.NzG + k]);
+            dst[(size_t)j * P.Nz() + (k - P.k0)] = v;
+        }
+    return DFB_OK;
+}
+
+int dfb_filter(dfb_handle h, double dt) {
+    if (!h) return fail(DFB_ERR_ARG, "handle is NULL");
+    return guarded([&] { run_step(*h, dt, false); });
+}
+
+int dfb_first_step(dfb_handle h) {   // constructor semantics on demand (inject mode / after dfb_set_state(.., 0))
+    if (!h) return fail(DFB_ERR_ARG, "handle is NULL");
+    return guarded([&] { run_step(*h, 0.0, true); });
+}
+
+int dfb_get_field(dfb_handle h, int which, double* dst, int dst_on_device) {
+    if (!h || !dst) return fail(DFB_ERR_ARG, "handle/dst is NULL");
+    const double* src = field_ptr(*h, which);
+    if (!src) return fail(DFB_ERR_ARG, "unknown field selector");
+    return guarded([&] {
+        CUDA_TRY(cudaSetDevice(h->device));
+        const size_t bytes = sizeof(double) * (size_t)h->D.Ny * h->D.W;
+        CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, dst_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+    });
+}
+
+int dfb_filter_to_host(dfb_handle h, double dt, double* u, double* v, double* w, double* T, double* rho) {
+    if (!h) return fail(DFB_ERR_ARG, "handle is NULL");
+    return guarded([&] {
+        run_step(*h, dt, false);
+        const size_t bytes = sizeof(double) * (size_t)h->D.Ny * h->D.W;
+        double* dst[5] = {u, v, w, T, rho};
+        for (int i = 0; i < 5; ++i)
+            if (dst[i]) CUDA_TRY(cudaMemcpyAsync(dst[i], field_ptr(*h, i), bytes, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+    });
+}
+
+int dfb_filter_batch(dfb_handle h, int nsteps, const double* dt, double* out) {
+    if (!h || !dt || nsteps < 0) return fail(DFB_ERR_ARG, "bad argument");
+    return guarded([&] {
+        const size_t n = (size_t)h->D.Ny * h->D.W;
+        for (int s = 0; s < nsteps; ++s) {
+            run_step(*h, dt[s], false);
+            if (out)
+                for (int i = 0; i < 5; ++i)
+                    CUDA_TRY(cudaMemcpyAsync(out + ((size_t)s * 5 + i) * n, field_ptr(*h, i), n * sizeof(double),
+                                             cudaMemcpyDeviceToHost, h->stream));
+        }
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+    });
+}
+
+int dfb_device_ptr(dfb_handle h, int which, void** ptr) {
+    if (!h || !ptr) return fail(DFB_ERR_ARG, "handle/ptr is NULL");
+    const double* p = field_ptr(*h, which);
+    if (!p) return fail(DFB_ERR_ARG, "unknown field selector");
+    *ptr = const_cast<double*>(p);
+    return DFB_OK;
+}
+
+int dfb_stream(dfb_handle h, void** stream) {
+    if (!h || !stream) return fail(DFB_ERR_ARG, "handle/stream is NULL");
+    *stream = h->stream;
+    return DFB_OK;
+}
+
+int dfb_sync(dfb_handle h) {
+    if (!h) return fail(DFB_ERR_ARG, "handle is NULL");
+    return guarded([&] { CUDA_TRY(cudaSetDevice(h->device)); CUDA_TRY(cudaStreamSynchronize(h->stream)); });
+}
+
+static int set_noise_impl(dfb_handle h, int field, const double* r_ys, const double* left, const double* right, size_t halo_pitch) {
+    if (!h || !r_ys || field < 0 || field > 2) return fail(DFB_ERR_ARG, "bad argument");
+    if (h->noise_mode != DFB_NOISE_INJECT) return fail(DFB_ERR_STATE, "handle was not created with noise_mode = DFB_NOISE_INJECT");
+    return guarded([&] {
+        CUDA_TRY(cudaSetDevice(h->device));
+        const FieldDev& F = h->D.f[field];
+        const int W = h->D.W, M = F.Nz_max;
+        CUDA_TRY(cudaMemcpy2DAsync(F.r_ys, (size_t)F.pitch_y * 8, r_ys, (size_t)W * 8, (size_t)W * 8, (size_t)F.rows_y,
+                                   cudaMemcpyHostToDevice, h->stream));
+        if (M > 0) {
+            if (!left || !right) throw Error{DFB_ERR_ARG, "halo noise missing"};
+            CUDA_TRY(cudaMemcpy2DAsync(F.r_zs + F.zoff, (size_t)F.pitch_z * 8, left, halo_pitch, (size_t)M * 8, (size_t)h->D.Ny,
+                                       cudaMemcpyHostToDevice, h->stream));
+            CUDA_TRY(cudaMemcpy2DAsync(F.r_zs + F.zoff + W + M, (size_t)F.pitch_z * 8, right, halo_pitch, (size_t)M * 8,
+                                       (size_t)h->D.Ny, cudaMemcpyHostToDevice, h->stream));
+        }
+        CUDA_TRY(cudaStreamSynchronize(h->stream));   // the caller may reuse its buffers
+        h->injected[field] = true;
+    });
+}
+
+int dfb_set_noise(dfb_handle h, int field, const double* r_ys, const double* r_zs_halo) {
+    if (!h || field < 0 || field > 2) return fail(DFB_ERR_ARG, "bad argument");
+    const int M = h->D.f[field].Nz_max;
+    return set_noise_impl(h, field, r_ys, r_zs_halo, r_zs_halo ? r_zs_halo + M : nullptr, (size_t)2 * M * 8);
+}
+
+int dfb_set_noise_ref_layout(dfb_handle h, int field, const double* r_ys, const double* r_zs) {
+    if (!h || field < 0 || field > 2) return fail(DFB_ERR_ARG, "bad argument");
+    const int M = h->D.f[field].Nz_max, W = h->D.W;
+    return set_noise_impl(h, field, r_ys, r_zs, r_zs ? r_zs + W + M : nullptr, (size_t)(W + 2 * M) * 8);
+}
+
+int dfb_get_noise(dfb_handle h, int field, double* r_ys, double* r_zs_halo) {
+    if (!h || field < 0 || field > 2) return fail(DFB_ERR_ARG, "bad argument");
+    if (h->plan.k0 != 0 || h->plan.k1 != h->plan.NzG) return fail(DFB_ERR_STATE, "dfb_get_noise is defined on whole-plane handles");
+    return guarded([&] {
+        CUDA_TRY(cudaSetDevice(h->device));
+        const FieldDev& F = h->D.f[field];
+        const int W = h->D.W, M = F.Nz_max;
+        if (r_ys)
+            CUDA_TRY(cudaMemcpy2DAsync(r_ys, (size_t)W * 8, F.r_ys, (size_t)F.pitch_y * 8, (size_t)W * 8, (size_t)F.rows_y,
+                                       cudaMemcpyDeviceToHost, h->stream));
+        if (r_zs_halo && M > 0) {
+            CUDA_TRY(cudaMemcpy2DAsync(r_zs_halo, (size_t)2 * M * 8, F.r_zs + F.zoff, (size_t)F.pitch_z * 8, (size_t)M * 8,
+                                       (size_t)h->D.Ny, cudaMemcpyDeviceToHost, h->stream));
+            CUDA_TRY(cudaMemcpy2DAsync(r_zs_halo + M, (size_t)2 * M * 8, F.r_zs + F.zoff + W + M, (size_t)F.pitch_z * 8, (size_t)M * 8,
+                                       (size_t)h->D.Ny, cudaMemcpyDeviceToHost, h->stream));
+        }
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+    });
+}
+
+int dfb_generate_noise(dfb_handle h, int64_t step) {
+    if (!h || step < 0) return fail(DFB_ERR_ARG, "bad argument");
+    return guarded([&] {
+        CUDA_TRY(cudaSetDevice(h->device));
+        fill_noise_params(*h, step);
+        CUDA_TRY(launch_noise(h->np, h->D, h->stream));
+    });
+}
+
+int dfb_get_state(dfb_handle h, double* filt_old3, int64_t* step) {
+    if (!h) return fail(DFB_ERR_ARG, "handle is NULL");
+    return guarded([&] {
+        CUDA_TRY(cudaSetDevice(h->device));
+        const size_t n = (size_t)h->D.Ny * h->D.W;
+        if (filt_old3)
+            for (int f = 0; f < 3; ++f)
+                CUDA_TRY(cudaMemcpyAsync(filt_old3 + f * n, h->D.f[f].filt_old, n * 8, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        if (step) *step = h->step;
+    });
+}
+
+int dfb_set_state(dfb_handle h, const double* filt_old3, int64_t step) {
+    if (!h || step < 0) return fail(DFB_ERR_ARG, "bad argument");
+    return guarded([&] {
+        CUDA_TRY(cudaSetDevice(h->device));
+        const size_t n = (size_t)h->D.Ny * h->D.W;
+        if (filt_old3)
+            for (int f = 0; f < 3; ++f)
+                CUDA_TRY(cudaMemcpyAsync(h->D.f[f].filt_old, filt_old3 + f * n, n * 8, cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        h->step = step;
+    });
+}
+
+int dfb_set_timing(dfb_handle h, int on) {
+    if (!h) return fail(DFB_ERR_ARG, "handle is NULL");
+    h->timing = on != 0;
+    return DFB_OK;
+}
+
+int dfb_last_ms(dfb_handle h, int stage, float* ms) {
+    if (!h || !ms || stage < 0 || stage > 3) return fail(DFB_ERR_ARG, "bad argument");
+    *ms = h->last_ms[stage];
+    return DFB_OK;
+}
+
+int dfb_measure_fp64_peak(int device, double* tflops, double* sm_mhz_est) {
+    if (!tflops) return fail(DFB_ERR_ARG, "tflops is NULL");
+    return guarded([&] {
+        if (device >= 0) CUDA_TRY(cudaSetDevice(device));
+        int dev = 0;
+        CUDA_TRY(cudaGetDevice(&dev));
+        cudaDeviceProp prop;
+        CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+        const int blocks = prop.multiProcessorCount * 8;
+        double* d = nullptr;
+        CUDA_TRY(cudaMalloc(&d, sizeof(double) * (size_t)blocks * 256));
+        cudaEvent_t a, b;
+        CUDA_TRY(cudaEventCreate(&a)); CUDA_TRY(cudaEventCreate(&b));
+        const int iters = 4096;
+        float best = 1e30f;
+        for (int rep = 0; rep < 6; ++rep) {
+            CUDA_TRY(cudaEventRecord(a, 0));
+            CUDA_TRY(launch_dfma_peak(d, blocks, iters, 0));
+            CUDA_TRY(cudaEventRecord(b, 0));
+            CUDA_TRY(cudaEventSynchronize(b));
+            float ms = 0;
+            CUDA_TRY(cudaEventElapsedTime(&ms, a, b));
+            if (rep >= 2) best = std::min(best, ms);
+        }
+        const double fma = (double)blocks * 256.0 * iters * 64.0;
+        *tflops = 2.0 * fma / (best * 1e-3) / 1e12;
+        if (sm_mhz_est) *sm_mhz_est = fma / (best * 1e-3) / (prop.multiProcessorCount * 64.0) / 1e6;   // if 64 DFMA/clk/SM
+        cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(d);
+    });
+}
+
+const char* dfb_last_error(void) { return g_last_error.c_str(); }
+const char* dfb_version(void) { return "dfb200 0.1 (sm_100a; rng spec v1)"; }
+
+int dfb_create_f(const dfb_config* cfg, dfb_handle* out) { return dfb_create(cfg, out); }
+int dfb_filter_f(const dfb_handle* h, const double* dt) { return (h && dt) ? dfb_filter(*h, *dt) : fail(DFB_ERR_ARG, "NULL argument"); }
+int dfb_filter_to_host_f(const dfb_handle* h, const double* dt, double* u, double* v, double* w, double* T, double* rho) {
+    return (h && dt) ? dfb_filter_to_host(*h, *dt, u, v, w, T, rho) : fail(DFB_ERR_ARG, "NULL argument");
+}
+int dfb_dims_f(const dfb_handle* h, int* Ny, int* Nz) { return h ? dfb_dims(*h, Ny, Nz) : fail(DFB_ERR_ARG, "NULL argument"); }
+int dfb_destroy_f(dfb_handle* h) {
+    if (!h) return DFB_OK;
+    int rc = dfb_destroy(*h);
+    *h = nullptr;
+    return rc;
+}
+
+}  // extern "C"

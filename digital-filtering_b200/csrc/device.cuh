@@ -1,0 +1,108 @@
+// csrc/device.cuh -- device-side data layout of one inflow plane (or one spanwise slab of it) in HBM.
+//
+//   r_ys[f]   (Ny + 2*Ny_max[f]) x pitch_y   white noise of the y-sweep (df.cpp:197), columns = the slab's
+//                                            EXTENDED range [xk0, xk1) = [k0-Nz_max, k1+Nz_max) clipped to the plane
+//   r_zs[f]   Ny x pitch_z                   logical column c in [0, W+2*Nz_max) lives at zoff + c; c = Nz_max is
+//                                            the slab's first column (df.cpp:157,363).  Columns whose GLOBAL
+//                                            index falls outside [0,NzG) hold raw noise,
+//                                            the others are written by the y-sweep (incl. neighbours' columns,
+//                                            recomputed locally instead of exchanged).
+//   filt_old[f], fluc[f], T, rho   dense Ny x W, row-major j*W + k  (df.cpp:106) -> one memcpy to the caller
+//   coefficients: one row per distinct half-width N (CSR keyed by N), plus per-row-group dense band
+//   matrices for the tuned y-sweep; per-row epilogue constants.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include <cuda.h>
+
+namespace dfb {
+
+constexpr int YJ = 8;          // output rows per thread / per row group of the tuned y-sweep
+constexpr int Y_TK = 512;      // columns per y-sweep tile (4 consumer warps x 128)
+constexpr int Z_KC = 8;        // consecutive outputs per thread of the tuned z-sweep
+constexpr int Z_TK = 1024;     // columns per z-sweep tile (4 warps x 32 lanes x Z_KC)
+
+struct FieldDev {
+    int Ny_max, Nz_max;
+    int rows_y;            // Ny + 2*Ny_max
+    int We, xk0;           // extended column count, global index of extended column 0
+    int pitch_y;           // doubles
+    int pitch_z, zoff;     // doubles
+    int yshift;            // extended column x -> r_zs logical column x + yshift
+    double* r_ys;
+    double* r_zs;
+    double* filt_old;
+    double* fluc;
+    const int* Ny_row;     // [Ny]
+    const int* Nz_row;     // [Ny]
+    const int* Ny_cell;    // [Ny*NzG] or nullptr (row-uniform)
+    const int* Nz_cell;
+};
+
+// per-row constants of the fused epilogue, computed on the host with the reference's expressions
+// (df.cpp:425-438, 474): {sqrt(R11), b, sqrt(R22-b*b), sqrt(R33), temp1, Ts, rhos, pad}
+constexpr int ROWC = 8;
+
+struct PlaneDev {
+    int Ny, W, NzG, k0;
+    FieldDev f[3];
+    double* T_fluc;
+    double* rho_fluc;
+    const double* rowc;        // [Ny][ROWC]
+    const int64_t* coef_ptr;   // [Nmax+1]
+    const double* coef_vals;
+};
+
+// ---- tuned y-sweep work description ----
+struct YGroup {                // YJ consecutive output rows of one field
+    int field, j0, nrows, Nmax;
+    int row0;                  // first padded input row of the window = j0 + Ny_max - Nmax
+    int nchunks;               // window length / RC
+    long long cmat_off;        // doubles, into the band-matrix pool
+};
+struct YItem { int group, col0; };
+
+struct YMaps { CUtensorMap m[3]; };
+
+struct StepConsts {
+    double sa[3], sb[3];       // sqrt(alpha), sqrt(1-alpha) per field (df.cpp:412-415), from the host's exp/sqrt
+    int first_step;            // constructor semantics (df.cpp:57-62): no blend, T'/rho' untouched
+};
+
+// ---- noise generation work description (one segment = one row of one logical array) ----
+struct NoiseArray {
+    uint64_t state;            // pcg32 state at the first draw of this step's array
+    uint64_t inc;
+    const void* seg_jump;      // Jump[n_seg]: jump from `state` to the segment's first pair
+    const long long* seg_q0;   // first pair index of each segment (global pair index within the array)
+    const int* seg_np;         // pairs in each segment
+    int n_seg;
+    int kind;                  // 0 = r_ys rows, 1 = r_zs halo rows
+    int field;
+};
+
+struct Jump;   // noise.cuh
+
+struct NoiseParams {
+    NoiseArray a[6];
+    const Jump* slot_jump;      // (A, G) for delta = 4*t: state' = A*state + inc*G
+    int n_arrays;
+    int max_np;                 // largest segment (pairs)
+    int chunks;                 // ceil(max_np / 128)
+};
+
+struct YParams {
+    const YGroup* groups;
+    const YItem* items;
+    const double* cmat;
+    PlaneDev D;
+};
+
+struct ZParams {
+    PlaneDev D;
+    StepConsts S;
+    int max_len;        // samples per field window in smem: Z_TK + 8 + round_up(2*max(Nz_max), 8)
+    int max_coef;       // coefficient slots per field: 2*max(Nz_max) + 32
+};
+
+}  // namespace dfb

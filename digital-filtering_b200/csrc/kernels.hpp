@@ -1,0 +1,19 @@
+// csrc/kernels.hpp -- host launchers of the kernels in kernels.cu
+#pragma once
+#include "device.cuh"
+
+namespace dfb {
+
+cudaError_t launch_noise(const NoiseParams& P, const PlaneDev& D, cudaStream_t st);
+cudaError_t launch_ysweep_simple(const PlaneDev& D, cudaStream_t st);
+cudaError_t launch_zsweep_simple(const PlaneDev& D, const StepConsts& S, cudaStream_t st);
+size_t ysweep_smem_bytes();
+int ysweep_rc();
+cudaError_t ysweep_prepare();
+cudaError_t launch_ysweep_tma(const YMaps& maps, const YParams& P, int n_items, cudaStream_t st);
+size_t zsweep_smem_bytes(int max_len, int max_coef);
+cudaError_t zsweep_prepare(size_t smem);
+cudaError_t launch_zsweep_tuned(const ZParams& P, cudaStream_t st);
+cudaError_t launch_dfma_peak(double* out, int blocks, int iters, cudaStream_t st);
+
+}  // namespace dfb

@@ -1,0 +1,96 @@
+// csrc/noise.cuh -- device side of the white-noise contract in include/dfb_rng_spec.h (spec v1).
+// Replaces DIGITAL_FILTER::generate_white_noise (df.cpp:332-349): per-element pcg32 streams
+// (pcg_random.hpp:1866) addressed by jump-ahead (pcg_random.hpp:640-669) instead of one serial
+// process-wide stream, and a Box-Muller pair transform made only of correctly rounded IEEE
+// operations so that the host restatement (oracle/normal_oracle.c) matches bit for bit.
+#pragma once
+#include <cstdint>
+#include "dfb_rng_spec.h"
+
+namespace dfb {
+
+struct Jump { uint64_t A, C; };   // state' = A*state + C
+
+__host__ __device__ inline uint64_t pcg_lcg(uint64_t s, uint64_t inc) { return s * DFB_PCG32_MULT + inc; }
+
+// XSH-RR 64 -> 32 (pcg_random.hpp:845-872)
+__host__ __device__ inline uint32_t pcg_xsh_rr(uint64_t s) {
+    uint32_t x = (uint32_t)(((s >> 18) ^ s) >> 27);
+    uint32_t r = (uint32_t)(s >> 59);
+#ifdef __CUDA_ARCH__
+    return __funnelshift_r(x, x, r);
+#else
+    return (x >> r) | (x << ((32u - r) & 31u));
+#endif
+}
+
+// Brown's arbitrary-stride jump (pcg_random.hpp:640-669) as a composable affine map
+inline Jump pcg_jump(uint64_t delta, uint64_t inc) {
+    uint64_t acc_mult = 1u, acc_plus = 0u, cur_mult = DFB_PCG32_MULT, cur_plus = inc;
+    while (delta > 0) {
+        if (delta & 1u) { acc_mult *= cur_mult; acc_plus = acc_plus * cur_mult + cur_plus; }
+        cur_plus = (cur_mult + 1u) * cur_plus;
+        cur_mult *= cur_mult;
+        delta >>= 1;
+    }
+    return Jump{acc_mult, acc_plus};
+}
+
+#ifdef __CUDACC__
+__constant__ double c_log[DFB_LOG_NC] = {DFB_LOG_C_LIST};
+__constant__ double c_sin[DFB_SIN_NC] = {DFB_SIN_C_LIST};
+__constant__ double c_cos[DFB_COS_NC] = {DFB_COS_C_LIST};
+
+// Four draws starting at `state` -> (z0, z1).  Every floating-point operation is an explicit
+// round-to-nearest intrinsic: nvcc may not contract, reorder or substitute anything.
+__device__ __forceinline__ void normal_pair(uint64_t state, uint64_t inc, double& z0, double& z1) {
+    uint32_t o0 = pcg_xsh_rr(state); state = pcg_lcg(state, inc);
+    uint32_t o1 = pcg_xsh_rr(state); state = pcg_lcg(state, inc);
+    uint32_t o2 = pcg_xsh_rr(state); state = pcg_lcg(state, inc);
+    uint32_t o3 = pcg_xsh_rr(state);
+    uint64_t U1 = ((((uint64_t)o1 << 32) | o0) >> 11) + 1u;
+    uint64_t U2 = (((uint64_t)o3 << 32) | o2) >> 11;
+
+    double d = __ull2double_rn(U1);                         // exact: U1 <= 2^53
+    uint64_t bits = (uint64_t)__double_as_longlong(d);
+    int E = (int)(bits >> 52) - 1023;
+    double m = __longlong_as_double((long long)((bits & 0x000FFFFFFFFFFFFFULL) | 0x3FF0000000000000ULL));
+    if (m > DFB_SQRT2) { m = __dmul_rn(m, 0.5); E += 1; }
+    double f = __dadd_rn(m, -1.0);
+    double s = __ddiv_rn(f, __dadd_rn(2.0, f));
+    double zz = __dmul_rn(s, s);
+    double P = c_log[DFB_LOG_NC - 1];
+#pragma unroll
+    for (int k = DFB_LOG_NC - 2; k >= 0; --k) P = __fma_rn(P, zz, c_log[k]);
+    double lnm = __fma_rn(__dmul_rn(s, zz), P, __dmul_rn(2.0, s));
+    double lnu = __fma_rn((double)(E - 53), DFB_LN2, lnm);
+    double r = __dsqrt_rn(__dmul_rn(-2.0, lnu));
+
+    unsigned oct = (unsigned)(U2 >> 50);
+    uint64_t T = U2 & ((1ULL << 50) - 1u);
+    if (oct & 1u) T = (1ULL << 50) - T;
+    double t = __dmul_rn(__ull2double_rn(T), 0x1p-50);
+    double x = __dmul_rn(t, DFB_PIO4);
+    double x2 = __dmul_rn(x, x);
+    double S = c_sin[DFB_SIN_NC - 1];
+#pragma unroll
+    for (int k = DFB_SIN_NC - 2; k >= 0; --k) S = __fma_rn(S, x2, c_sin[k]);
+    double sx = __fma_rn(__dmul_rn(x, x2), S, x);
+    double Cc = c_cos[DFB_COS_NC - 1];
+#pragma unroll
+    for (int k = DFB_COS_NC - 2; k >= 0; --k) Cc = __fma_rn(Cc, x2, c_cos[k]);
+    double cx = __fma_rn(x2, Cc, 1.0);
+    if (oct & 1u) { double tmp = sx; sx = cx; cx = tmp; }
+    double sn, cs;
+    switch (oct >> 1) {
+        case 0:  sn =  sx; cs =  cx; break;
+        case 1:  sn =  cx; cs = -sx; break;
+        case 2:  sn = -sx; cs = -cx; break;
+        default: sn = -cx; cs =  sx; break;
+    }
+    z0 = __dmul_rn(r, cs);
+    z1 = __dmul_rn(r, sn);
+}
+#endif  // __CUDACC__
+
+}  // namespace dfb

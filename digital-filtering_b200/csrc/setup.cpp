@@ -1,0 +1,287 @@
+// csrc/setup.cpp -- one-time host setup: the part of DIGITAL_FILTER::DIGITAL_FILTER (df.cpp:4-66) that
+// runs before the first sweep.  It is executed once per handle, on the host, with the host's libm
+// (exp / tanh / sqrt), exactly like the reference, so that no device transcendental ever enters
+// the parity gate (SURVEY 8c "third-party arithmetic").  Expression order follows the cited lines:
+// the resulting tables are bit-identical to the reference object's (tests/test_setup_parity.py).
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <algorithm>
+#include "plan.hpp"
+
+namespace dfb {
+
+namespace {
+
+constexpr double pi_c = -2.0 * 3.14159265358979323846;   // df.hpp:16
+
+std::string cstr(const char* p, int len) {
+    if (!p) return std::string();
+    if (len < 0) return std::string(p);
+    std::string s(p, p + len);
+    while (!s.empty() && (s.back() == ' ' || s.back() == '\0')) s.pop_back();   // Fortran blank padding
+    return s;
+}
+
+// One VARIABLES line, one "ZONE ... i=N" line, then rows of whitespace-separated numbers
+// (df.cpp:231-278 and 498-537 parse both files this way).
+std::vector<std::vector<double>> read_zone_file(const std::string& path, int& n_rows) {
+    std::ifstream fin(path);
+    if (!fin) throw Error{DFB_ERR_IO, "cannot open input file '" + path + "' (df.cpp:225/492)"};
+    std::string line;
+    std::getline(fin, line);
+    std::getline(fin, line);
+    double n_in = 0;
+    size_t pos = line.find("i=");
+    if (pos == std::string::npos) throw Error{DFB_ERR_IO, "no 'i=' count on line 2 of '" + path + "'"};
+    {
+        std::istringstream iss(line.substr(pos + 2));
+        iss >> n_in;
+    }
+    n_rows = (int)n_in;
+    if (n_rows < 2) throw Error{DFB_ERR_INTERP, "Need at least two data points to interpolate. (" + path + ")"};
+    std::vector<std::vector<double>> rows;
+    while (std::getline(fin, line)) {
+        if (line.empty()) continue;
+        std::istringstream iss(line);
+        std::vector<double> v;
+        double x;
+        while (iss >> x) v.push_back(x);
+        if (v.empty()) continue;
+        if ((int)rows.size() < n_rows) rows.push_back(std::move(v));
+    }
+    if ((int)rows.size() < n_rows)
+        throw Error{DFB_ERR_IO, "'" + path + "' announces more rows than it holds"};
+    return rows;
+}
+
+}  // namespace
+
+// df.cpp:805-848
+std::vector<double> linear_interpolate(const std::vector<double>& y_data, const std::vector<double>& f_data,
+                                       const std::vector<double>& y_new) {
+    if (y_data.size() != f_data.size()) throw Error{DFB_ERR_INTERP, "y_data and f_data must be the same size."};
+    if (y_data.size() < 2) throw Error{DFB_ERR_INTERP, "Need at least two data points to interpolate."};
+    std::vector<double> f_new(y_new.size());
+    for (size_t j = 0; j < y_new.size(); ++j) {
+        double y = y_new[j];
+        if (y <= y_data.front()) { f_new[j] = f_data.front(); continue; }
+        if (y >= y_data.back()) { f_new[j] = f_data.back(); continue; }
+        size_t i = 0;
+        while (i + 1 < y_data.size() && y > y_data[i + 1]) ++i;
+        double x0 = y_data[i], x1 = y_data[i + 1], f0 = f_data[i], f1 = f_data[i + 1];
+        f_new[j] = f0 + (f1 - f0) * ((y - x0) / (x1 - x0));
+    }
+    return f_new;
+}
+
+// df.cpp:166-177 == 202-216
+void coefficients(int N, double* b) {
+    std::vector<double> temp(N + 1);
+    double sum = 0.0;
+    for (int i = 0; i <= N; ++i) {
+        temp[i] = std::exp(pi_c * std::abs(i) / N);
+        sum += (i == 0 ? 1.0 : 2.0) * temp[i] * temp[i];
+    }
+    sum = std::sqrt(sum);
+    for (int i = -N; i <= N; ++i) b[N + i] = temp[std::abs(i)] / sum;
+}
+
+void build_plan(const dfb_config& cfg, Plan& P) {
+    // ---- flow constants: df.cpp:7-16 (the C++ reference ignores DFConfig); df.f90:80-87 honours it
+    if (cfg.honor_flow_config) {
+        if (!(cfg.d_i > 0) || !(cfg.U_e > 0)) throw Error{DFB_ERR_ARG, "honor_flow_config needs d_i > 0 and U_e > 0"};
+        P.d_i = cfg.d_i; P.rho_e = cfg.rho_e; P.U_e = cfg.U_e; P.mu = cfg.mu_e;
+    } else {
+        P.d_i = 0.0013; P.rho_e = 0.044; P.U_e = 869.1; P.mu = 7.1212e-6;
+    }
+    P.gcon = 287.0;
+    const double d_i = P.d_i;
+
+    // ---- geometry: read_grid, df.cpp:71-118 ----
+    const bool default_grid = (cfg.Ny == 0 && cfg.Nz == 0);
+    int Ny, NzG;
+    bool per_row;
+    std::vector<double> yc, dy, dz;   // per row or per cell
+    if (default_grid) {
+        Ny = 560; NzG = 400; per_row = true;                     // df.cpp:73-74
+        std::vector<double> y(Ny + 1);
+        double y_max = 3 * d_i, a = 2.0;                          // df.cpp:92-94
+        for (int j = Ny; j >= 0; --j) {
+            double eta = ((j) * y_max / (Ny + 1)) / y_max;        // df.cpp:98
+            y[std::abs(j - Ny)] = y_max * (1 - std::tanh(a * eta) / std::tanh(a));   // df.cpp:99
+        }
+        yc.resize(Ny); dy.resize(Ny); dz.assign(Ny, 0.000133);    // df.cpp:108
+        for (int j = 0; j < Ny; ++j) {
+            dy[j] = y[j + 1] - y[j];                              // df.cpp:107
+            yc[j] = 0.25 * (y[j] + y[j + 1] + y[j] + y[j + 1]);   // df.cpp:109-112 (grid is z-independent)
+        }
+    } else {
+        if (cfg.Ny <= 0 || cfg.Nz <= 0) throw Error{DFB_ERR_ARG, "Ny and Nz must both be positive (or both 0)"};
+        Ny = cfg.Ny; NzG = cfg.Nz; per_row = cfg.geom_per_row != 0;
+        const bool explicit_N = cfg.N_y && cfg.N_z;
+        if (!explicit_N && (!cfg.yc || !cfg.dy || !cfg.dz))
+            throw Error{DFB_ERR_ARG, "explicit plane needs yc/dy/dz or N_y/N_z"};
+        size_t n = per_row ? (size_t)Ny : (size_t)Ny * NzG;
+        if (cfg.yc) yc.assign(cfg.yc, cfg.yc + n);
+        if (cfg.dy) dy.assign(cfg.dy, cfg.dy + n);
+        if (cfg.dz) dz.assign(cfg.dz, cfg.dz + n);
+        if (!cfg.rows && yc.empty()) throw Error{DFB_ERR_ARG, "interpolating the row tables from files needs yc"};
+    }
+    const size_t gstride = per_row ? 1 : (size_t)NzG;   // index of (j, k=0) = j*gstride
+
+    // ---- row tables: get_RST_in df.cpp:220-330, read_line_file df.cpp:487-553 ----
+    if (cfg.rows) {
+        P.rows.assign(cfg.rows, cfg.rows + (size_t)8 * Ny);
+    } else {
+        std::string rst_path = cstr(cfg.vel_fluc_file, cfg.vel_fluc_file_len);
+        if (rst_path.empty()) rst_path = "../files/RST.dat";      // df.cpp:224
+        std::string line_path = cstr(cfg.line_file, cfg.line_file_len);
+        if (line_path.empty()) line_path = "../line.dat";          // df.cpp:16
+        int N_in = 0;
+        auto rst = read_zone_file(rst_path, N_in);
+        std::vector<double> yin_d(N_in), urms(N_in), vrms(N_in), wrms(N_in), uv(N_in);
+        for (int i = 0; i < N_in; ++i) {
+            if (rst[i].size() < 6) throw Error{DFB_ERR_IO, "'" + rst_path + "': fewer than 6 columns"};
+            yin_d[i] = rst[i][1]; urms[i] = rst[i][2]; vrms[i] = rst[i][3]; wrms[i] = rst[i][4]; uv[i] = rst[i][5];   // :270-275
+        }
+        // trim Ny to the rows inside the DNS data, df.cpp:282-288
+        int new_Ny = 0;
+        while (new_Ny < Ny && yc[(size_t)new_Ny * gstride] / d_i <= yin_d[N_in - 1]) new_Ny++;
+        if (new_Ny < 2) throw Error{DFB_ERR_ARG, "fewer than 2 rows lie inside the fluctuation file's y/delta range"};
+        if (new_Ny != Ny) {
+            Ny = new_Ny;
+            size_t n = per_row ? (size_t)Ny : (size_t)Ny * NzG;
+            yc.resize(n); dy.resize(n); if (dz.size() > n) dz.resize(n);
+        }
+        std::vector<double> yline(Ny), ydline(Ny);
+        for (int j = 0; j < Ny; ++j) { yline[j] = yc[(size_t)j * gstride]; ydline[j] = yline[j] / d_i; }   // :113-116
+
+        int N_line = 0;
+        auto ln = read_zone_file(line_path, N_line);
+        std::vector<double> y_file(N_line), rho_file(N_line), u_file(N_line), T_file(N_line);
+        for (int i = 0; i < N_line; ++i) {
+            if (ln[i].size() < 10) throw Error{DFB_ERR_IO, "'" + line_path + "': fewer than 10 columns"};
+            y_file[i] = ln[i][1]; rho_file[i] = ln[i][4]; u_file[i] = ln[i][5]; T_file[i] = ln[i][8];   // :530-534
+        }
+        auto Us = linear_interpolate(y_file, u_file, yline);       // :539
+        auto Ts = linear_interpolate(y_file, T_file, yline);       // :541
+        auto rhos = linear_interpolate(y_file, rho_file, yline);   // :542
+        std::vector<double> Ms(Ny);
+        for (int j = 0; j < Ny; ++j) Ms[j] = Us[j] / std::sqrt(1.4 * P.gcon * Ts[j]);   // :544
+        double dyf = y_file[1] - y_file[0];                        // :547
+        double du = Us[1] - Us[0];
+        P.tau_w = P.mu * du / dyf;
+        P.u_tau = std::sqrt(P.tau_w / rhos[0]);
+        const double u_tau = P.u_tau;
+        std::vector<double> R11_in(N_in), R22_in(N_in), R33_in(N_in), R21_in(N_in);
+        for (int j = 0; j < N_in; ++j) {                           // :312-317
+            R11_in[j] = urms[j] * urms[j] * u_tau * u_tau;
+            R22_in[j] = vrms[j] * vrms[j] * u_tau * u_tau;
+            R33_in[j] = wrms[j] * wrms[j] * u_tau * u_tau;
+            R21_in[j] = uv[j] * u_tau * u_tau;
+        }
+        auto R11 = linear_interpolate(yin_d, R11_in, ydline);      // :320-323
+        auto R22 = linear_interpolate(yin_d, R22_in, ydline);
+        auto R21 = linear_interpolate(yin_d, R21_in, ydline);
+        auto R33 = linear_interpolate(yin_d, R33_in, ydline);
+        P.rows.resize((size_t)8 * Ny);
+        const std::vector<double>* src[8] = {&R11, &R21, &R22, &R33, &Us, &Ts, &rhos, &Ms};
+        for (int t = 0; t < 8; ++t) std::copy(src[t]->begin(), src[t]->end(), P.rows.begin() + (size_t)t * Ny);
+    }
+    P.Ny = Ny; P.NzG = NzG;
+    P.d_v = d_i / 4500;                                            // df.cpp:326
+    P.yc_row.resize(Ny); P.dy_row.resize(Ny);
+    for (int j = 0; j < Ny; ++j) {
+        P.yc_row[j] = yc.empty() ? 0.0 : yc[(size_t)j * gstride];
+        P.dy_row[j] = dy.empty() ? 0.0 : dy[(size_t)j * gstride];
+    }
+
+    // ---- slab ----
+    if (cfg.k_begin == 0 && cfg.k_end == 0) { P.k0 = 0; P.k1 = NzG; }
+    else {
+        if (cfg.k_begin < 0 || cfg.k_end > NzG || cfg.k_begin >= cfg.k_end)
+            throw Error{DFB_ERR_ARG, "slab [k_begin,k_end) must lie inside [0,Nz)"};
+        P.k0 = cfg.k_begin; P.k1 = cfg.k_end;
+    }
+
+    // ---- integral scales, df.cpp:35-45 ----
+    if (cfg.scales) {
+        for (int f = 0; f < 3; ++f) { P.f[f].Iz_inn = cfg.scales[3 * f]; P.f[f].Iz_out = cfg.scales[3 * f + 1]; P.f[f].Lt = cfg.scales[3 * f + 2]; }
+    } else {
+        P.f[0].Iz_out = 0.4 * d_i; P.f[0].Iz_inn = 150 * P.d_v; P.f[0].Lt = 0.8 * d_i / P.U_e;
+        P.f[1].Iz_out = 0.3 * d_i; P.f[1].Iz_inn = 75 * P.d_v;  P.f[1].Lt = 0.3 * d_i / P.U_e;
+        P.f[2].Iz_out = 0.4 * d_i; P.f[2].Iz_inn = 150 * P.d_v; P.f[2].Lt = 0.3 * d_i / P.U_e;
+    }
+    for (int f = 0; f < 3; ++f)
+        if (!(P.f[f].Lt > 0)) throw Error{DFB_ERR_ARG, "Lagrangian time scale Lt must be positive"};
+
+    // ---- half-widths: calculate_filter_properties, df.cpp:144-154 and 186-195 ----
+    const size_t ncol = per_row ? 1 : (size_t)NzG;
+    for (int f = 0; f < 3; ++f) {
+        FieldPlan& F = P.f[f];
+        std::vector<int> Ny_arr((size_t)Ny * ncol), Nz_arr((size_t)Ny * ncol);
+        if (cfg.N_y && cfg.N_z) {
+            const int* sy = cfg.N_y + (size_t)f * Ny * ncol;
+            const int* sz = cfg.N_z + (size_t)f * Ny * ncol;
+            for (size_t i = 0; i < Ny_arr.size(); ++i) {
+                if (sy[i] < 0 || sz[i] < 0) throw Error{DFB_ERR_ARG, "half-widths must be >= 0"};
+                Ny_arr[i] = sy[i]; Nz_arr[i] = sz[i];
+            }
+        } else {
+            for (size_t idx = 0; idx < Ny_arr.size(); ++idx) {
+                double Iz = F.Iz_inn + (F.Iz_out - F.Iz_inn) * 0.5 * (1 + std::tanh((yc[idx] / d_i - 0.2) / 0.03));   // :146
+                double n_int = std::max(1.0, Iz / dz[idx]);        // :147
+                Nz_arr[idx] = 2 * static_cast<int>(n_int);         // :148
+                double Iy = 0.67 * Iz;                             // :187
+                n_int = std::max(1.0, Iy / dy[idx]);               // :188
+                Ny_arr[idx] = 2 * static_cast<int>(n_int);         // :189
+            }
+        }
+        F.Ny_max = *std::max_element(Ny_arr.begin(), Ny_arr.end());   // :153,194 (over the whole plane)
+        F.Nz_max = *std::max_element(Nz_arr.begin(), Nz_arr.end());
+        F.row_uniform = true;
+        F.N_y_row.resize(Ny); F.N_z_row.resize(Ny);
+        for (int j = 0; j < Ny; ++j) {
+            F.N_y_row[j] = Ny_arr[(size_t)j * ncol]; F.N_z_row[j] = Nz_arr[(size_t)j * ncol];
+            for (size_t k = 1; k < ncol && F.row_uniform; ++k)
+                if (Ny_arr[(size_t)j * ncol + k] != F.N_y_row[j] || Nz_arr[(size_t)j * ncol + k] != F.N_z_row[j])
+                    F.row_uniform = false;
+        }
+        if (!F.row_uniform) { F.N_y = std::move(Ny_arr); F.N_z = std::move(Nz_arr); }
+    }
+
+    // ---- coefficient table keyed by N ----
+    int Nmax = 0;
+    for (int f = 0; f < 3; ++f) Nmax = std::max({Nmax, P.f[f].Ny_max, P.f[f].Nz_max});
+    std::vector<char> present(Nmax + 1, 0);
+    for (int f = 0; f < 3; ++f) {
+        const FieldPlan& F = P.f[f];
+        if (F.row_uniform) { for (int j = 0; j < Ny; ++j) { present[F.N_y_row[j]] = 1; present[F.N_z_row[j]] = 1; } }
+        else { for (int v : F.N_y) present[v] = 1; for (int v : F.N_z) present[v] = 1; }
+    }
+    P.coef.Nmax = Nmax;
+    P.coef.ptr.assign(Nmax + 1, -1);
+    int64_t total = 0;
+    for (int N = 0; N <= Nmax; ++N) if (present[N]) { P.coef.ptr[N] = total; total += 2 * N + 1; }
+    P.coef.vals.resize(total);
+    for (int N = 0; N <= Nmax; ++N) if (present[N]) {
+        if (N == 0) P.coef.vals[P.coef.ptr[0]] = 1.0;   // only reachable through explicit N arrays
+        else coefficients(N, P.coef.vals.data() + P.coef.ptr[N]);
+    }
+
+    // ---- algorithmic work of one step on the local slab (F_alg = 2 * taps) ----
+    P.taps_per_step = 0;
+    for (int f = 0; f < 3; ++f) {
+        const FieldPlan& F = P.f[f];
+        for (int j = 0; j < Ny; ++j) {
+            if (F.row_uniform) P.taps_per_step += (int64_t)(P.k1 - P.k0) * ((2 * F.N_y_row[j] + 1) + (2 * F.N_z_row[j] + 1));
+            else for (int k = P.k0; k < P.k1; ++k)
+                P.taps_per_step += (2 * F.N_y[(size_t)j * NzG + k] + 1) + (2 * F.N_z[(size_t)j * NzG + k] + 1);
+        }
+    }
+}
+
+}  // namespace dfb
