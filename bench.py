@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py -- inflow cell-updates/s per filter() step (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl b200|reference]
+
+One "step" = one DIGITAL_FILTER::filter(dt) (df.cpp:449-468) over one synthetic plane: noise generation,
+y-sweep, z-sweep, temporal blend, RST scaling, SRA -- all five outputs of every cell.
+  value    whole-job cell-updates/s, state resident in HBM, CUDA events on the library's stream
+  e2e      the same through the reference-facing call (dfb_filter_to_host: filter(dt) + the five
+           fields copied into pinned HOST arrays, as the C++/Fortran facades do every step)
+  roofline the dominant kernel against the fp64-FMA roof measured live (DFMA microbenchmark in the
+           library; MEASURED_PEAKS.json has no fp64 entry) and the step against the HBM roof
+  cpu_baseline  the reference's own df.cpp (oracle/_ref) on the box's host, bounded sample
+N > 1 (torchrun): every rank filters its own independent plane (distinct RNG stream group = rank):
+weak scaling, no data-path collective; time = max over ranks.
+--impl reference: the reference's CPU filter() on all host cores (independent processes; the
+reference is single-threaded with a process-wide RNG), same metric/config, bounded sample per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DEFAULT_WORKLOAD = "1024x2048_profile_N128"
+METRIC = "inflow cell-updates/sec per filter() step"
+DT = 1e-7
+
+
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.p, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for ln in self.p.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.p:
+            return None
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=2)
+        except Exception:
+            self.p.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            c = [x.strip() for x in ln.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        busy = [s for s in sm if s > 0.5 * max(sm)] or sm
+        return dict(sm_mhz=float(np.median(busy)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's own df.cpp on a bounded sample of the workload
+# --------------------------------------------------------------------------------------------------
+def sample_plane(plane, target_taps=4.0e8):
+    """A spanwise sub-slab of the same plane (same rows, same half-width profile, fewer columns)
+    sized for ~1 s of single-core CPU work per step."""
+    from oracle import oracle as O
+    p = dict(plane)
+    O.half_widths(p)
+    taps_per_col = float(sum((2 * p["N_y"][f][:, 0].astype(np.int64) + 1).sum() + (2 * p["N_z"][f][:, 0].astype(np.int64) + 1).sum() for f in range(3)))
+    ncol = int(max(8, min(plane["Nz"], target_taps // taps_per_col)))
+    s = dict(plane)
+    s["Nz"] = ncol
+    s["name"] = plane["name"] + f"[sample:{plane['Ny']}x{ncol}]"
+    return s, taps_per_col * ncol
+
+
+def _ref_worker(args):
+    plane, steps, warmup = args
+    from oracle import oracle as O
+    R = O.RefFilter()
+    R.reshape(plane)
+    R.time_steps(DT, warmup)
+    tot, st = R.time_steps(DT, steps)
+    R.close()
+    return tot
+
+
+def cpu_reference_run(plane, steps, warmup, nproc):
+    """nproc independent reference objects, one process each; returns (seconds for `steps` steps, kind)."""
+    from oracle import oracle as O
+    if O.have_ref():
+        import multiprocessing as mp
+        if nproc == 1:
+            return _ref_worker((plane, steps, warmup)), "reference"
+        with mp.get_context("fork").Pool(nproc) as pool:
+            ts = pool.map(_ref_worker, [(plane, steps, warmup)] * nproc)
+        return max(ts), "reference"
+    # fall-back checker: the plain-C restatement (single instance, OpenMP over rows)
+    p = dict(plane)
+    O.half_widths(p)
+    Ny, Nz = p["Ny"], p["Nz"]
+    rys = [O.noise_rys(1, 0, f, 0, Ny, p["Ny_max"][f], Nz) for f in range(3)]
+    hal = [O.noise_halo(1, 0, f, 0, Ny, p["Nz_max"][f]) for f in range(3)]
+    fo = np.zeros((3, Ny, Nz))
+    for _ in range(warmup):
+        O.step(p, rys, hal, fo, DT)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.step(p, rys, hal, fo, DT)
+    return time.perf_counter() - t0, "port"
+
+
+def run_reference_arm(args, plane):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ncores = os.cpu_count() or 1
+    nproc = max(1, min(ncores, 32))
+    s, taps = sample_plane(plane, target_taps=2.0e8)
+    secs, kind = cpu_reference_run(s, args.steps, min(args.warmup, 1), nproc)
+    cells = s["Ny"] * s["Nz"] * nproc * args.steps
+    value = cells / secs
+    line = dict(impl="reference", metric=METRIC, value=value, unit="cell-updates/s", n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=1e3 * secs / args.steps, higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="f64", data="synthetic",
+                config=dict(workload=plane["name"], plane=[plane["Ny"], plane["Nz"]], dt=DT),
+                cpu_baseline=dict(value=value, unit="cell-updates/s", cores=nproc if kind == "reference" else ncores, kind=kind,
+                                  sample=f"{nproc} independent instances x ({s['Ny']}x{s['Nz']} sub-slab of the {plane['Ny']}x{plane['Nz']} plane, same rows/half-widths)"
+                                         f" per step; the reference's five stage calls (df.cpp:453-461), no print/CSV"),
+                e2e=dict(value=value, unit="cell-updates/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# B200 arm
+# --------------------------------------------------------------------------------------------------
+def run_b200(args, plane):
+    import torch
+    import _dfb_import  # noqa: F401
+    import digital_filtering_b200 as dfb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 arm has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    K, Wm = args.steps, max(args.warmup, 3)
+    df = dfb.DIGITAL_FILTER(dfb.DFConfig.from_plane(plane, seed=20261018, plane_id=rank, device=local), fetch=False)
+    assert df.tuned, "tuned sm_100a kernels must be the measured path"
+    stream = torch.cuda.ExternalStream(df.stream(), device=local)
+    cells = df.n_cells
+    N_y = [df.half_widths(f, 0) for f in range(3)]
+    N_z = [df.half_widths(f, 1) for f in range(3)]
+    taps_y = int(sum((2 * a.astype(np.int64) + 1).sum() for a in N_y))
+    taps_z = int(sum((2 * a.astype(np.int64) + 1).sum() for a in N_z))
+    ws_bytes = 8 * (sum((plane["Ny"] + 2 * int(a.max())) * plane["Nz"] for a in N_y) + 3 * cells + 11 * cells)
+    l2_bytes = 126 * 2 ** 20
+    flush = ws_bytes < 2 * l2_bytes
+    fbuf = torch.empty(256 * 2 ** 20, dtype=torch.uint8, device="cuda") if flush else None
+
+    # ---- value: device-resident steps, CUDA events on the library's stream ----
+    for _ in range(Wm):
+        df.filter(DT)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    for i in range(K):
+        if flush:
+            with torch.cuda.stream(stream):
+                fbuf.zero_()
+        ev[i][0].record(stream)
+        df.filter(DT)
+        ev[i][1].record(stream)
+    df.sync()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = world * cells * K / (ms_total * 1e-3)
+
+    # ---- e2e: filter(dt) + five fields into pinned host arrays, every step ----
+    host = [torch.empty(cells, dtype=torch.float64).pin_memory() for _ in range(5)]
+    hp = [h.data_ptr() for h in host]
+    L = dfb.lib()
+    for _ in range(2):
+        dfb._check(L.dfb_filter_to_host(df._h, DT, *hp))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        dfb._check(L.dfb_filter_to_host(df._h, DT, *hp))
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * cells * K / float(te.item())
+
+    if rank != 0:
+        df.close()
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- per-kernel times (CUDA events inside the library, one sync per step: explains, not the headline) ----
+    df.set_timing(True)
+    stage = []
+    for _ in range(max(5, min(K, 20))):
+        if flush:
+            with torch.cuda.stream(stream):
+                fbuf.zero_()
+        df.filter(DT)
+        stage.append(df.last_ms())
+    df.set_timing(False)
+    med = {k: float(np.median([s[k] for s in stage])) for k in stage[0]}
+    fp64_peak, mhz = dfb.measure_fp64_peak(local)
+    peaks = load_peaks()
+    hbm_peak = peaks["hbm_gbs"] if peaks and "hbm_gbs" in peaks else 6650.0
+    hbm_src = "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"
+    kern = {
+        "ysweep_tma_kernel": dict(ms=med["ysweep"], tflops=2 * taps_y / (med["ysweep"] * 1e-3) / 1e12),
+        "zsweep_epilogue_kernel": dict(ms=med["zsweep_epilogue"], tflops=2 * taps_z / (med["zsweep_epilogue"] * 1e-3) / 1e12),
+        "noise_kernel": dict(ms=med["noise"]),
+    }
+    for k in ("ysweep_tma_kernel", "zsweep_epilogue_kernel"):
+        kern[k]["frac_fp64"] = kern[k]["tflops"] / fp64_peak
+    dom = "ysweep_tma_kernel" if med["ysweep"] >= med["zsweep_epilogue"] else "zsweep_epilogue_kernel"
+    alg_bytes = 88 * cells                                    # 5 outputs + filt_old r/w x3
+    step_ms = ms_total / K
+    roofline = dict(bound="fp64", kernel=dom, achieved=kern[dom]["tflops"], peak=fp64_peak, unit="TFLOP/s", frac=kern[dom]["frac_fp64"],
+                    traffic=None, peak_source="DFMA microbenchmark measured live in this run (dfb_measure_fp64_peak); MEASURED_PEAKS.json has no fp64 entry",
+                    step=dict(tflops=2 * (taps_y + taps_z) / (step_ms * 1e-3) / 1e12, frac_fp64=2 * (taps_y + taps_z) / (step_ms * 1e-3) / 1e12 / fp64_peak,
+                              hbm_gbs=alg_bytes / (step_ms * 1e-3) / 1e9, frac_hbm=alg_bytes / (step_ms * 1e-3) / 1e9 / hbm_peak, hbm_peak=hbm_peak,
+                              hbm_peak_source=hbm_src, binding="fp64" if 2 * (taps_y + taps_z) / fp64_peak / 1e12 > alg_bytes / hbm_peak / 1e9 else "hbm"),
+                    kernels=kern)
+
+    # ---- cpu baseline: the reference's own df.cpp, 1 core, bounded sample ----
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        try:
+            s, _ = sample_plane(plane)
+            nst = 5
+            secs, kind = cpu_reference_run(s, nst, 1, 1)
+            cpu = dict(value=s["Ny"] * s["Nz"] * nst / secs, unit="cell-updates/s", cores=1 if kind == "reference" else (os.cpu_count() or 1), kind=kind,
+                       sample=f"{nst} steps of a {s['Ny']}x{s['Nz']} spanwise sub-slab of the {plane['Ny']}x{plane['Nz']} plane (same rows, same half-widths); "
+                              f"the reference's five stage calls (df.cpp:453-461), 1 of {os.cpu_count()} host cores", ms_per_step_sample=1e3 * secs / nst)
+        except Exception as e:   # the checker is optional for the bench; say so rather than die
+            cpu = dict(value=None, unit="cell-updates/s", cores=0, kind="unavailable", sample=str(e)[:200])
+
+    line = dict(metric=METRIC, value=value, unit="cell-updates/s", n_gpus=world, steps=K, warmup=Wm, ms_per_step=step_ms,
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+                config=dict(workload=plane["name"], plane=[plane["Ny"], plane["Nz"]], max_half_width=[int(max(a.max() for a in N_y)), int(max(a.max() for a in N_z))],
+                            taps_per_cell=(taps_y + taps_z) / cells, dt=DT, noise="generate (counter-based pcg32, spec v1)",
+                            l2="flushed between steps (256 MiB write)" if flush else f"per-step working set {ws_bytes / 2**20:.0f} MiB > 126 MiB L2, no flush",
+                            parallelism=f"{world} independent plane(s), one per GPU"),
+                clocks=clocks, gpu_launches=3 * K, wall_ms_per_step=1e3 * t_wall / K,
+                e2e=dict(value=e2e_value, unit="cell-updates/s", h2d_bytes_per_step=8, d2h_bytes_per_step=40 * cells,
+                         call="dfb_filter_to_host (filter(dt) + u',v',w',T',rho' into pinned host arrays); input is the scalar dt"),
+                roofline=roofline, cpu_baseline=cpu)
+    print(json.dumps(line), flush=True)
+    df.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    import _dfb_import  # noqa: F401
+    from digital_filtering_b200 import workloads as W
+    if args.workload not in W.NAMED:
+        raise SystemExit(f"unknown workload {args.workload}; choose from {sorted(W.NAMED)}")
+    plane = W.NAMED[args.workload]()
+    if args.impl == "reference":
+        run_reference_arm(args, plane)
+    else:
+        run_b200(args, plane)
+
+
+if __name__ == "__main__":
+    main()
