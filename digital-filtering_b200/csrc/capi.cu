@@ -52,15 +52,23 @@ struct dfb_filter_s {
     int plane_id = 0;
     int64_t step = 0;                 // steps completed (the constructor's first step counts as one)
     bool injected[3] = {false, false, false};
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;    // main stream (high priority): sweeps + epilogue
+    cudaStream_t side = nullptr;      // low-priority stream: next step's noise, generated while this step filters
     std::vector<void*> allocs;
-    PlaneDev D{};
+    // Two noise buffer sets (r_ys, r_zs): step s uses set s&1, so noise(s+1) can be written while
+    // y(s)/z(s) still read set s&1.  D[b] differs from D[1-b] only in the r_ys / r_zs pointers.
+    PlaneDev D[2]{};
+    bool overlap = true;
+    int64_t buf_step[2] = {-1, -1};   // which step's noise set b currently holds (or -1)
+    int noise_view = 0;               // set holding the most recently consumed / generated noise
+    cudaEvent_t ev_noise[2] = {nullptr, nullptr};   // noise into set b complete (either stream)
+    cudaEvent_t ev_free[2] = {nullptr, nullptr};    // last readers of set b complete (main stream)
     // tuned y-sweep
-    YMaps maps{};
-    YParams yp{};
+    YMaps maps[2]{};
+    YParams yp[2]{};
     int n_items = 0;
     // tuned z-sweep
-    ZParams zp{};
+    ZParams zp[2]{};
     // noise
     std::vector<NoiseHost> noise;
     NoiseParams np{};
@@ -85,9 +93,12 @@ struct dfb_filter_s {
     }
     ~dfb_filter_s() {
         cudaSetDevice(device);
+        if (side) cudaStreamSynchronize(side);
         if (stream) cudaStreamSynchronize(stream);
         for (void* p : allocs) cudaFree(p);
         for (auto& e : ev) if (e) cudaEventDestroy(e);
+        for (int b = 0; b < 2; ++b) { if (ev_noise[b]) cudaEventDestroy(ev_noise[b]); if (ev_free[b]) cudaEventDestroy(ev_free[b]); }
+        if (side) cudaStreamDestroy(side);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -112,7 +123,7 @@ EncodeTiledFn encode_tiled() {
 
 void build_device(dfb_filter_s& H) {
     const Plan& P = H.plan;
-    PlaneDev& D = H.D;
+    PlaneDev& D = H.D[0];
     const int Ny = P.Ny, W = P.Nz(), NzG = P.NzG;
     D.Ny = Ny; D.W = W; D.NzG = NzG; D.k0 = P.k0;
     H.tuned = (H.kernel_variant == 0) && P.f[0].row_uniform && P.f[1].row_uniform && P.f[2].row_uniform;
@@ -161,60 +172,91 @@ void build_device(dfb_filter_s& H) {
         F.Ny_cell = FP.row_uniform ? nullptr : H.upload(FP.N_y);
         F.Nz_cell = FP.row_uniform ? nullptr : H.upload(FP.N_z);
     }
+    H.D[1] = H.D[0];
+    for (int f = 0; f < 3; ++f) {
+        H.D[1].f[f].r_ys = H.dalloc<double>((size_t)D.f[f].rows_y * D.f[f].pitch_y);
+        H.D[1].f[f].r_zs = H.dalloc<double>((size_t)Ny * D.f[f].pitch_z);
+    }
 
     // ---- tuned y-sweep: row groups, dense band matrices, work items, TMA maps ----
     if (H.tuned) {
         const int RC = ysweep_rc();
         std::vector<YGroup> groups;
+        std::vector<YTile> tiles;
         std::vector<double> cmat;
         for (int f = 0; f < 3; ++f) {
             const FieldPlan& FP = P.f[f];
+            const int first_group = (int)groups.size();
             for (int j0 = 0; j0 < Ny; j0 += YJ) {
                 YGroup g{};
                 g.field = f; g.j0 = j0; g.nrows = std::min(YJ, Ny - j0);
                 g.Nmax = 0;
                 for (int jj = 0; jj < g.nrows; ++jj) g.Nmax = std::max(g.Nmax, FP.N_y_row[j0 + jj]);
-                g.row0 = j0 + FP.Ny_max - g.Nmax;
-                const int T = g.nrows + 2 * g.Nmax;
-                g.nchunks = (T + RC - 1) / RC;
+                // padded input rows touched: output row j0+jj, tap i -> row j0 + jj + Ny_max + i  (df.cpp:362,374)
+                const int lo = j0 + FP.Ny_max - g.Nmax, hi = j0 + g.nrows - 1 + FP.Ny_max + g.Nmax;
+                g.cstart = lo / RC;
+                g.nchunks = hi / RC + 1 - g.cstart;
                 g.cmat_off = (long long)cmat.size();
                 cmat.resize(cmat.size() + (size_t)g.nchunks * RC * YJ, 0.0);
                 double* cm = cmat.data() + g.cmat_off;
                 for (int jj = 0; jj < g.nrows; ++jj) {
                     const int N = FP.N_y_row[j0 + jj];
                     const double* b = P.coef.centre(N);
-                    for (int i = -N; i <= N; ++i) cm[(size_t)(g.Nmax + jj + i) * YJ + jj] = b[i];
+                    for (int i = -N; i <= N; ++i)
+                        cm[(size_t)(j0 + jj + FP.Ny_max + i - g.cstart * RC) * YJ + jj] = b[i];
                 }
                 groups.push_back(g);
             }
+            const int ng = (int)groups.size() - first_group;
+            for (int gb = 0; gb < ng; gb += Y_G) {
+                YTile t{};
+                t.field = f; t.g0 = first_group + gb; t.ngroups = std::min(Y_G, ng - gb);
+                t.cbegin = 1 << 30; t.cend = 0;
+                for (int w = 0; w < t.ngroups; ++w) {
+                    const YGroup& g = groups[t.g0 + w];
+                    t.cbegin = std::min(t.cbegin, g.cstart);
+                    t.cend = std::max(t.cend, g.cstart + g.nchunks);
+                }
+                for (int c0 = 0; c0 < D.f[f].We; c0 += Y_TK) { t.col0 = c0; tiles.push_back(t); }
+            }
         }
-        std::vector<YItem> items;
-        for (int gi = 0; gi < (int)groups.size(); ++gi)
-            for (int c0 = 0; c0 < D.f[groups[gi].field].We; c0 += Y_TK) items.push_back(YItem{gi, c0});
-        std::stable_sort(items.begin(), items.end(), [&](const YItem& a, const YItem& b) {
-            return groups[a.group].nchunks > groups[b.group].nchunks;   // longest first
+        std::stable_sort(tiles.begin(), tiles.end(), [](const YTile& a, const YTile& b) {
+            return (a.cend - a.cbegin) > (b.cend - b.cbegin);   // longest first
         });
-        H.yp.groups = H.upload(groups);
-        H.yp.items = H.upload(items);
-        H.yp.cmat = H.upload(cmat);
-        H.yp.D = D;
-        H.n_items = (int)items.size();
+        H.yp[0].groups = H.upload(groups);
+        H.yp[0].tiles = H.upload(tiles);
+        H.yp[0].cmat = H.upload(cmat);
+        H.yp[0].D = H.D[0];
+        H.yp[1] = H.yp[0];
+        H.yp[1].D = H.D[1];
+        H.n_items = (int)tiles.size();
+        for (int b = 0; b < 2; ++b)
         for (int f = 0; f < 3; ++f) {
-            const FieldDev& F = D.f[f];
+            const FieldDev& F = H.D[b].f[f];
             cuuint64_t dims[2] = {(cuuint64_t)F.We, (cuuint64_t)F.rows_y};
             cuuint64_t strides[1] = {(cuuint64_t)F.pitch_y * sizeof(double)};
-            cuuint32_t box[2] = {128u, (cuuint32_t)RC};
+            cuuint32_t box[2] = {(cuuint32_t)Y_TK, (cuuint32_t)RC};
             cuuint32_t estr[2] = {1u, 1u};
-            CUresult r = encode_tiled()(&H.maps.m[f], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, F.r_ys, dims, strides, box, estr,
+            CUresult r = encode_tiled()(&H.maps[b].m[f], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, F.r_ys, dims, strides, box, estr,
                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) throw Error{DFB_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")"};
         }
         CUDA_TRY(ysweep_prepare());
-        H.zp.D = D;
-        H.zp.max_len = Z_TK + 8 + round_up(2 * maxNz, 8);
-        H.zp.max_coef = 2 * maxNz + 32;
-        CUDA_TRY(zsweep_prepare(zsweep_smem_bytes(H.zp.max_len, H.zp.max_coef)));
+        ZParams& Z = H.zp[0];
+        Z.D = H.D[0];
+        Z.kc = zsweep_kc(W);
+        Z.max_len = 128 * Z.kc + Z.kc + round_up(2 * maxNz, Z.kc);
+        Z.max_coef = 2 * maxNz + 3 * Z.kc;
+        Z.async_fill = 1;   // 16-byte cp.async staging needs every window start on an even column
+        for (int f = 0; f < 3; ++f) {
+            if (P.f[f].Nz_max & 1) Z.async_fill = 0;
+            for (int v : P.f[f].N_z_row) if (v & 1) Z.async_fill = 0;
+        }
+        CUDA_TRY(zsweep_prepare(Z.kc, zsweep_smem_bytes(Z.kc, Z.max_len, Z.max_coef)));
+        H.zp[1] = Z;
+        H.zp[1].D = H.D[1];
+        
     }
 
     // ---- noise tables (include/dfb_rng_spec.h) ----
@@ -278,18 +320,27 @@ void fill_noise_params(dfb_filter_s& H, int64_t step) {
     H.np.n_arrays = n;
 }
 
+void launch_noise_for(dfb_filter_s& H, int64_t step, int b, cudaStream_t st) {
+    fill_noise_params(H, step);
+    CUDA_TRY(launch_noise(H.np, H.D[b], st));
+    CUDA_TRY(cudaEventRecord(H.ev_noise[b], st));
+    H.buf_step[b] = step;
+}
+
 void run_step(dfb_filter_s& H, double dt, bool first) {
     CUDA_TRY(cudaSetDevice(H.device));
+    const int b = (int)(H.step & 1);
     if (H.timing) CUDA_TRY(cudaEventRecord(H.ev[0], H.stream));
     if (H.noise_mode == DFB_NOISE_GENERATE) {
-        fill_noise_params(H, H.step);
-        CUDA_TRY(launch_noise(H.np, H.D, H.stream));
+        if (H.buf_step[b] == H.step) CUDA_TRY(cudaStreamWaitEvent(H.stream, H.ev_noise[b], 0));   // prefetched
+        else launch_noise_for(H, H.step, b, H.stream);
     } else if (!(H.injected[0] && H.injected[1] && H.injected[2])) {
         throw Error{DFB_ERR_STATE, "noise_mode = inject: dfb_set_noise must be called for u, v and w before every step"};
     }
+    H.noise_view = b;
     if (H.timing) CUDA_TRY(cudaEventRecord(H.ev[1], H.stream));
-    if (H.tuned) CUDA_TRY(launch_ysweep_tma(H.maps, H.yp, H.n_items, H.stream));
-    else CUDA_TRY(launch_ysweep_simple(H.D, H.stream));
+    if (H.tuned) CUDA_TRY(launch_ysweep_tma(H.maps[b], H.yp[b], H.n_items, H.stream));
+    else CUDA_TRY(launch_ysweep_simple(H.D[b], H.stream));
     if (H.timing) CUDA_TRY(cudaEventRecord(H.ev[2], H.stream));
     StepConsts S{};
     S.first_step = first ? 1 : 0;
@@ -299,11 +350,19 @@ void run_step(dfb_filter_s& H, double dt, bool first) {
         S.sa[f] = std::sqrt(alpha);                                // df.cpp:415
         S.sb[f] = std::sqrt(1.0 - alpha);
     }
-    if (H.tuned) { H.zp.S = S; CUDA_TRY(launch_zsweep_tuned(H.zp, H.stream)); }
-    else CUDA_TRY(launch_zsweep_simple(H.D, S, H.stream));
+    if (H.tuned) { H.zp[b].S = S; CUDA_TRY(launch_zsweep_tuned(H.zp[b], H.stream)); }
+    else CUDA_TRY(launch_zsweep_simple(H.D[b], S, H.stream));
+    CUDA_TRY(cudaEventRecord(H.ev_free[b], H.stream));
     if (H.timing) CUDA_TRY(cudaEventRecord(H.ev[3], H.stream));
     H.step += 1;
     H.injected[0] = H.injected[1] = H.injected[2] = false;
+    // The noise of the NEXT step depends on nothing but (seed, step): generate it now, on the
+    // low-priority stream, into the other buffer set, while this step's sweeps own the fp64 pipe.
+    if (H.noise_mode == DFB_NOISE_GENERATE && H.overlap && !H.timing) {
+        const int nb = (int)(H.step & 1);
+        CUDA_TRY(cudaStreamWaitEvent(H.side, H.ev_free[nb], 0));     // readers of that set (step-2... ) are done
+        launch_noise_for(H, H.step, nb, H.side);
+    }
     if (H.timing) {
         CUDA_TRY(cudaEventSynchronize(H.ev[3]));
         for (int s = 0; s < 3; ++s) CUDA_TRY(cudaEventElapsedTime(&H.last_ms[s], H.ev[s], H.ev[s + 1]));
@@ -313,9 +372,9 @@ void run_step(dfb_filter_s& H, double dt, bool first) {
 
 const double* field_ptr(const dfb_filter_s& H, int which) {
     switch (which) {
-        case DFB_U_FLUC: return H.D.f[0].fluc;   case DFB_V_FLUC: return H.D.f[1].fluc;   case DFB_W_FLUC: return H.D.f[2].fluc;
-        case DFB_T_FLUC: return H.D.T_fluc;      case DFB_RHO_FLUC: return H.D.rho_fluc;
-        case DFB_U_FILT: return H.D.f[0].filt_old; case DFB_V_FILT: return H.D.f[1].filt_old; case DFB_W_FILT: return H.D.f[2].filt_old;
+        case DFB_U_FLUC: return H.D[0].f[0].fluc;   case DFB_V_FLUC: return H.D[0].f[1].fluc;   case DFB_W_FLUC: return H.D[0].f[2].fluc;
+        case DFB_T_FLUC: return H.D[0].T_fluc;      case DFB_RHO_FLUC: return H.D[0].rho_fluc;
+        case DFB_U_FILT: return H.D[0].f[0].filt_old; case DFB_V_FILT: return H.D[0].f[1].filt_old; case DFB_W_FILT: return H.D[0].f[2].filt_old;
     }
     return nullptr;
 }
@@ -376,8 +435,15 @@ int dfb_create(const dfb_config* cfg, dfb_handle* out) {
         build_plan(*cfg, H->plan);
         if (H->noise_mode == DFB_NOISE_INJECT && (H->plan.k0 != 0 || H->plan.k1 != H->plan.NzG))
             throw Error{DFB_ERR_ARG, "noise injection is defined on the whole plane (k_begin = k_end = 0)"};
-        CUDA_TRY(cudaStreamCreateWithFlags(&H->stream, cudaStreamNonBlocking));
+        int prio_lo = 0, prio_hi = 0;
+        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CUDA_TRY(cudaStreamCreateWithPriority(&H->stream, cudaStreamNonBlocking, prio_hi));
+        CUDA_TRY(cudaStreamCreateWithPriority(&H->side, cudaStreamNonBlocking, prio_lo));
         for (auto& e2 : H->ev) CUDA_TRY(cudaEventCreate(&e2));
+        for (int b = 0; b < 2; ++b) {
+            CUDA_TRY(cudaEventCreateWithFlags(&H->ev_noise[b], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&H->ev_free[b], cudaEventDisableTiming));
+        }
         build_device(*H);
         // first step of the constructor, df.cpp:57-62 (generate mode only: in inject mode the
         // caller owns the noise and runs it through dfb_first_step semantics via dfb_filter after
@@ -468,7 +534,7 @@ int dfb_get_field(dfb_handle h, int which, double* dst, int dst_on_device) {
     if (!src) return fail(DFB_ERR_ARG, "unknown field selector");
     return guarded([&] {
         CUDA_TRY(cudaSetDevice(h->device));
-        const size_t bytes = sizeof(double) * (size_t)h->D.Ny * h->D.W;
+        const size_t bytes = sizeof(double) * (size_t)h->D[0].Ny * h->D[0].W;
         CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, dst_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
         CUDA_TRY(cudaStreamSynchronize(h->stream));
     });
@@ -478,7 +544,7 @@ int dfb_filter_to_host(dfb_handle h, double dt, double* u, double* v, double* w,
     if (!h) return fail(DFB_ERR_ARG, "handle is NULL");
     return guarded([&] {
         run_step(*h, dt, false);
-        const size_t bytes = sizeof(double) * (size_t)h->D.Ny * h->D.W;
+        const size_t bytes = sizeof(double) * (size_t)h->D[0].Ny * h->D[0].W;
         double* dst[5] = {u, v, w, T, rho};
         for (int i = 0; i < 5; ++i)
             if (dst[i]) CUDA_TRY(cudaMemcpyAsync(dst[i], field_ptr(*h, i), bytes, cudaMemcpyDeviceToHost, h->stream));
@@ -489,7 +555,7 @@ int dfb_filter_to_host(dfb_handle h, double dt, double* u, double* v, double* w,
 int dfb_filter_batch(dfb_handle h, int nsteps, const double* dt, double* out) {
     if (!h || !dt || nsteps < 0) return fail(DFB_ERR_ARG, "bad argument");
     return guarded([&] {
-        const size_t n = (size_t)h->D.Ny * h->D.W;
+        const size_t n = (size_t)h->D[0].Ny * h->D[0].W;
         for (int s = 0; s < nsteps; ++s) {
             run_step(*h, dt[s], false);
             if (out)
@@ -525,16 +591,16 @@ static int set_noise_impl(dfb_handle h, int field, const double* r_ys, const dou
     if (h->noise_mode != DFB_NOISE_INJECT) return fail(DFB_ERR_STATE, "handle was not created with noise_mode = DFB_NOISE_INJECT");
     return guarded([&] {
         CUDA_TRY(cudaSetDevice(h->device));
-        const FieldDev& F = h->D.f[field];
-        const int W = h->D.W, M = F.Nz_max;
+        const FieldDev& F = h->D[h->step & 1].f[field];      // the set the next step reads
+        const int W = h->D[0].W, M = F.Nz_max;
         CUDA_TRY(cudaMemcpy2DAsync(F.r_ys, (size_t)F.pitch_y * 8, r_ys, (size_t)W * 8, (size_t)W * 8, (size_t)F.rows_y,
                                    cudaMemcpyHostToDevice, h->stream));
         if (M > 0) {
             if (!left || !right) throw Error{DFB_ERR_ARG, "halo noise missing"};
-            CUDA_TRY(cudaMemcpy2DAsync(F.r_zs + F.zoff, (size_t)F.pitch_z * 8, left, halo_pitch, (size_t)M * 8, (size_t)h->D.Ny,
+            CUDA_TRY(cudaMemcpy2DAsync(F.r_zs + F.zoff, (size_t)F.pitch_z * 8, left, halo_pitch, (size_t)M * 8, (size_t)h->D[0].Ny,
                                        cudaMemcpyHostToDevice, h->stream));
             CUDA_TRY(cudaMemcpy2DAsync(F.r_zs + F.zoff + W + M, (size_t)F.pitch_z * 8, right, halo_pitch, (size_t)M * 8,
-                                       (size_t)h->D.Ny, cudaMemcpyHostToDevice, h->stream));
+                                       (size_t)h->D[0].Ny, cudaMemcpyHostToDevice, h->stream));
         }
         CUDA_TRY(cudaStreamSynchronize(h->stream));   // the caller may reuse its buffers
         h->injected[field] = true;
@@ -543,13 +609,13 @@ static int set_noise_impl(dfb_handle h, int field, const double* r_ys, const dou
 
 int dfb_set_noise(dfb_handle h, int field, const double* r_ys, const double* r_zs_halo) {
     if (!h || field < 0 || field > 2) return fail(DFB_ERR_ARG, "bad argument");
-    const int M = h->D.f[field].Nz_max;
+    const int M = h->D[0].f[field].Nz_max;
     return set_noise_impl(h, field, r_ys, r_zs_halo, r_zs_halo ? r_zs_halo + M : nullptr, (size_t)2 * M * 8);
 }
 
 int dfb_set_noise_ref_layout(dfb_handle h, int field, const double* r_ys, const double* r_zs) {
     if (!h || field < 0 || field > 2) return fail(DFB_ERR_ARG, "bad argument");
-    const int M = h->D.f[field].Nz_max, W = h->D.W;
+    const int M = h->D[0].f[field].Nz_max, W = h->D[0].W;
     return set_noise_impl(h, field, r_ys, r_zs, r_zs ? r_zs + W + M : nullptr, (size_t)(W + 2 * M) * 8);
 }
 
@@ -558,16 +624,16 @@ int dfb_get_noise(dfb_handle h, int field, double* r_ys, double* r_zs_halo) {
     if (h->plan.k0 != 0 || h->plan.k1 != h->plan.NzG) return fail(DFB_ERR_STATE, "dfb_get_noise is defined on whole-plane handles");
     return guarded([&] {
         CUDA_TRY(cudaSetDevice(h->device));
-        const FieldDev& F = h->D.f[field];
-        const int W = h->D.W, M = F.Nz_max;
+        const FieldDev& F = h->D[h->noise_view].f[field];
+        const int W = h->D[0].W, M = F.Nz_max;
         if (r_ys)
             CUDA_TRY(cudaMemcpy2DAsync(r_ys, (size_t)W * 8, F.r_ys, (size_t)F.pitch_y * 8, (size_t)W * 8, (size_t)F.rows_y,
                                        cudaMemcpyDeviceToHost, h->stream));
         if (r_zs_halo && M > 0) {
             CUDA_TRY(cudaMemcpy2DAsync(r_zs_halo, (size_t)2 * M * 8, F.r_zs + F.zoff, (size_t)F.pitch_z * 8, (size_t)M * 8,
-                                       (size_t)h->D.Ny, cudaMemcpyDeviceToHost, h->stream));
+                                       (size_t)h->D[0].Ny, cudaMemcpyDeviceToHost, h->stream));
             CUDA_TRY(cudaMemcpy2DAsync(r_zs_halo + M, (size_t)2 * M * 8, F.r_zs + F.zoff + W + M, (size_t)F.pitch_z * 8, (size_t)M * 8,
-                                       (size_t)h->D.Ny, cudaMemcpyDeviceToHost, h->stream));
+                                       (size_t)h->D[0].Ny, cudaMemcpyDeviceToHost, h->stream));
         }
         CUDA_TRY(cudaStreamSynchronize(h->stream));
     });
@@ -577,8 +643,10 @@ int dfb_generate_noise(dfb_handle h, int64_t step) {
     if (!h || step < 0) return fail(DFB_ERR_ARG, "bad argument");
     return guarded([&] {
         CUDA_TRY(cudaSetDevice(h->device));
-        fill_noise_params(*h, step);
-        CUDA_TRY(launch_noise(h->np, h->D, h->stream));
+        const int b = (int)(step & 1);
+        CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_noise[b], 0));   // order after any prefetch into that set
+        launch_noise_for(*h, step, b, h->stream);
+        h->noise_view = b;
     });
 }
 
@@ -586,10 +654,10 @@ int dfb_get_state(dfb_handle h, double* filt_old3, int64_t* step) {
     if (!h) return fail(DFB_ERR_ARG, "handle is NULL");
     return guarded([&] {
         CUDA_TRY(cudaSetDevice(h->device));
-        const size_t n = (size_t)h->D.Ny * h->D.W;
+        const size_t n = (size_t)h->D[0].Ny * h->D[0].W;
         if (filt_old3)
             for (int f = 0; f < 3; ++f)
-                CUDA_TRY(cudaMemcpyAsync(filt_old3 + f * n, h->D.f[f].filt_old, n * 8, cudaMemcpyDeviceToHost, h->stream));
+                CUDA_TRY(cudaMemcpyAsync(filt_old3 + f * n, h->D[0].f[f].filt_old, n * 8, cudaMemcpyDeviceToHost, h->stream));
         CUDA_TRY(cudaStreamSynchronize(h->stream));
         if (step) *step = h->step;
     });
@@ -599,10 +667,10 @@ int dfb_set_state(dfb_handle h, const double* filt_old3, int64_t step) {
     if (!h || step < 0) return fail(DFB_ERR_ARG, "bad argument");
     return guarded([&] {
         CUDA_TRY(cudaSetDevice(h->device));
-        const size_t n = (size_t)h->D.Ny * h->D.W;
+        const size_t n = (size_t)h->D[0].Ny * h->D[0].W;
         if (filt_old3)
             for (int f = 0; f < 3; ++f)
-                CUDA_TRY(cudaMemcpyAsync(h->D.f[f].filt_old, filt_old3 + f * n, n * 8, cudaMemcpyHostToDevice, h->stream));
+                CUDA_TRY(cudaMemcpyAsync(h->D[0].f[f].filt_old, filt_old3 + f * n, n * 8, cudaMemcpyHostToDevice, h->stream));
         CUDA_TRY(cudaStreamSynchronize(h->stream));
         h->step = step;
     });

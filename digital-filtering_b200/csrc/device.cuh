@@ -18,9 +18,8 @@
 namespace dfb {
 
 constexpr int YJ = 8;          // output rows per thread / per row group of the tuned y-sweep
-constexpr int Y_TK = 512;      // columns per y-sweep tile (4 consumer warps x 128)
-constexpr int Z_KC = 8;        // consecutive outputs per thread of the tuned z-sweep
-constexpr int Z_TK = 1024;     // columns per z-sweep tile (4 warps x 32 lanes x Z_KC)
+constexpr int Y_G = 4;         // row groups (consumer warps) per y-sweep tile: 32 output rows share one sample stream
+constexpr int Y_TK = 128;      // columns per y-sweep tile (each lane owns 4 of them)
 
 struct FieldDev {
     int Ny_max, Nz_max;
@@ -56,11 +55,14 @@ struct PlaneDev {
 // ---- tuned y-sweep work description ----
 struct YGroup {                // YJ consecutive output rows of one field
     int field, j0, nrows, Nmax;
-    int row0;                  // first padded input row of the window = j0 + Ny_max - Nmax
-    int nchunks;               // window length / RC
-    long long cmat_off;        // doubles, into the band-matrix pool
+    int cstart;                // first chunk of the window on the field's absolute chunk grid (chunk c = padded rows [c*RC, (c+1)*RC))
+    int nchunks;               // chunks the window touches
+    long long cmat_off;        // doubles, into the band-matrix pool: Cmat[(row - cstart*RC)][YJ]
 };
-struct YItem { int group, col0; };
+struct YTile {                 // up to Y_G consecutive groups x Y_TK columns
+    int field, col0, g0, ngroups;
+    int cbegin, cend;          // union of the groups' chunk ranges
+};
 
 struct YMaps { CUtensorMap m[3]; };
 
@@ -93,7 +95,7 @@ struct NoiseParams {
 
 struct YParams {
     const YGroup* groups;
-    const YItem* items;
+    const YTile* tiles;
     const double* cmat;
     PlaneDev D;
 };
@@ -101,8 +103,10 @@ struct YParams {
 struct ZParams {
     PlaneDev D;
     StepConsts S;
-    int max_len;        // samples per field window in smem: Z_TK + 8 + round_up(2*max(Nz_max), 8)
-    int max_coef;       // coefficient slots per field: 2*max(Nz_max) + 32
+    int kc;             // consecutive outputs per thread: 16 (wide planes) or 8; the CTA covers 128*kc columns
+    int max_len;        // samples per field window in smem: 128*kc + kc + round_up(2*max(Nz_max), kc)
+    int max_coef;       // coefficient slots per field: 2*max(Nz_max) + 3*kc
+    int async_fill;     // 1: every N_z is even -> 16-byte cp.async staging; 0: scalar staging
 };
 
 }  // namespace dfb

@@ -163,86 +163,109 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
 // =================================================================================================
 // H2y tuned: y-sweep for row-uniform half-widths.
 //
-// One CTA = one row group (YJ = 8 consecutive output rows of one field) x 512 columns.
-// Warp 4 is the TMA producer: it streams the window of input rows [row0, row0 + nchunks*RC) through
-// a ring of NS shared-memory stages (cp.async.bulk.tensor.2d, 128-column boxes) together with the
-// matching RC x 8 slice of the group's dense band matrix (cp.async.bulk).  Warps 0-3 are consumers:
-// lane l owns columns {2l, 2l+1, 64+2l, 65+2l} of its 128-column strip and all 8 rows, i.e. 32 fp64
-// accumulators in registers; per input row it issues 2 LDS.128 (samples, conflict-free) + 4 LDS.128
-// (coefficients, warp-broadcast) for 32 DFMA.  out[jj] += C[t][jj] * x[t] -- the band matrix holds
-// b_{N(jj)}[t - jj - Nmax] and exact zeros outside each row's own half-width, so rows of different
-// N share one pass (adds of +0*x leave the sum unchanged; noise is finite).
+// One CTA = Y_G = 4 row groups (32 consecutive output rows of one field) x 128 columns.
+// Warp 4 is the TMA producer: it streams the union of the groups' input-row windows, chunk by
+// chunk (RC = 8 padded rows x 128 columns, one cp.async.bulk.tensor.2d box), through a ring of NS
+// shared-memory stages, together with the matching RC x 8 slice of each active group's dense band
+// matrix (cp.async.bulk).  Sharing one sample stream between 4 groups cuts the L2 -> SM traffic
+// from (8+2N)/8 to (32+2N)/32 loads per output.  Warps 0-3 are the consumers, one row group each:
+// lane l owns columns {2l, 2l+1, 64+2l, 65+2l} and the group's 8 rows = 32 fp64 accumulators in
+// registers; per input row it issues 2 LDS.128 (samples, conflict-free) + 4 LDS.128 (coefficients,
+// warp-broadcast) for 32 DFMA.  out[jj] += C[t][jj] * x[t]: the band matrix holds b_{N(jj)}[t-..]
+// and exact zeros outside each row's own half-width, so rows of different N share one pass
+// (adding +0*x leaves a sum unchanged; noise is finite).
 // =================================================================================================
 template <int RC, int NS>
 struct YSmem {
-    double samples[NS][4][RC][128];
-    double coefs[NS][RC][YJ];
+    double samples[NS][RC][Y_TK];
+    double coefs[NS][Y_G][RC][YJ];
     uint64_t full[NS];
     uint64_t empty[NS];
 };
 
 template <int RC, int NS>
-__global__ void __launch_bounds__(160) ysweep_tma_kernel(const __grid_constant__ YMaps maps, const YParams P) {
+__global__ void __launch_bounds__(160, 3) ysweep_tma_kernel(const __grid_constant__ YMaps maps, const YParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     YSmem<RC, NS>& sm = *reinterpret_cast<YSmem<RC, NS>*>(smem_raw);
-    const YItem it = P.items[blockIdx.x];
-    const YGroup g = P.groups[it.group];
-    const FieldDev& F = P.D.f[g.field];
+    const YTile t = P.tiles[blockIdx.x];
+    const FieldDev& F = P.D.f[t.field];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NS; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 4); }
+        for (int s = 0; s < NS; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], Y_G); }
         mbar_fence_init();
     }
     __syncthreads();
 
-    if (warp == 4) {
+    if (warp == Y_G) {
         if (lane == 0) {
-            const CUtensorMap* map = &maps.m[g.field];
-            constexpr uint32_t kBytes = (uint32_t)(sizeof(double) * (4 * RC * 128 + RC * YJ));
-            for (int c = 0; c < g.nchunks; ++c) {
-                const int s = c % NS;
-                if (c >= NS) mbar_wait(&sm.empty[s], ((c / NS) - 1) & 1);
-                mbar_expect_tx(&sm.full[s], kBytes);
-                const int row = g.row0 + c * RC;
+            const CUtensorMap* map = &maps.m[t.field];
+            int cs[Y_G], ce[Y_G];
+            const double* cm[Y_G];
 #pragma unroll
-                for (int w = 0; w < 4; ++w) tma_load_2d(&sm.samples[s][w][0][0], map, it.col0 + 128 * w, row, &sm.full[s]);
-                tma_load_1d(&sm.coefs[s][0][0], P.cmat + g.cmat_off + (long long)c * RC * YJ, RC * YJ * sizeof(double), &sm.full[s]);
+            for (int w = 0; w < Y_G; ++w) {
+                if (w < t.ngroups) {
+                    const YGroup g = P.groups[t.g0 + w];
+                    cs[w] = g.cstart; ce[w] = g.cstart + g.nchunks; cm[w] = P.cmat + g.cmat_off;
+                } else { cs[w] = 0; ce[w] = 0; cm[w] = nullptr; }
+            }
+            int i = 0;
+            for (int c = t.cbegin; c < t.cend; ++c, ++i) {
+                const int s = i % NS;
+                if (i >= NS) mbar_wait(&sm.empty[s], ((i / NS) - 1) & 1);
+                uint32_t bytes = (uint32_t)(sizeof(double) * RC * Y_TK);
+#pragma unroll
+                for (int w = 0; w < Y_G; ++w) if (c >= cs[w] && c < ce[w]) bytes += (uint32_t)(sizeof(double) * RC * YJ);
+                mbar_expect_tx(&sm.full[s], bytes);
+                tma_load_2d(&sm.samples[s][0][0], map, t.col0, c * RC, &sm.full[s]);
+#pragma unroll
+                for (int w = 0; w < Y_G; ++w)
+                    if (c >= cs[w] && c < ce[w])
+                        tma_load_1d(&sm.coefs[s][w][0][0], cm[w] + (long long)(c - cs[w]) * RC * YJ, RC * YJ * sizeof(double), &sm.full[s]);
             }
         }
         return;
     }
 
+    const bool have = warp < t.ngroups;
+    YGroup g{};
+    if (have) g = P.groups[t.g0 + warp];
+    const int my_cs = have ? g.cstart : 0, my_ce = have ? g.cstart + g.nchunks : 0;
+
     double acc[YJ][4];
 #pragma unroll
     for (int jj = 0; jj < YJ; ++jj) { acc[jj][0] = acc[jj][1] = acc[jj][2] = acc[jj][3] = 0.0; }
 
-    for (int c = 0; c < g.nchunks; ++c) {
-        const int s = c % NS;
-        mbar_wait(&sm.full[s], (c / NS) & 1);
+    int i = 0;
+    for (int c = t.cbegin; c < t.cend; ++c, ++i) {
+        const int s = i % NS;
+        mbar_wait(&sm.full[s], (i / NS) & 1);
+        if (c >= my_cs && c < my_ce) {
 #pragma unroll
-        for (int r = 0; r < RC; ++r) {
-            const double2 xa = *reinterpret_cast<const double2*>(&sm.samples[s][warp][r][2 * lane]);
-            const double2 xb = *reinterpret_cast<const double2*>(&sm.samples[s][warp][r][64 + 2 * lane]);
+            for (int r = 0; r < RC; ++r) {
+                const double2 xa = *reinterpret_cast<const double2*>(&sm.samples[s][r][2 * lane]);
+                const double2 xb = *reinterpret_cast<const double2*>(&sm.samples[s][r][64 + 2 * lane]);
 #pragma unroll
-            for (int jj = 0; jj < YJ; jj += 2) {
-                const double2 cc = *reinterpret_cast<const double2*>(&sm.coefs[s][r][jj]);
-                acc[jj][0] = fma(cc.x, xa.x, acc[jj][0]);
-                acc[jj][1] = fma(cc.x, xa.y, acc[jj][1]);
-                acc[jj][2] = fma(cc.x, xb.x, acc[jj][2]);
-                acc[jj][3] = fma(cc.x, xb.y, acc[jj][3]);
-                acc[jj + 1][0] = fma(cc.y, xa.x, acc[jj + 1][0]);
-                acc[jj + 1][1] = fma(cc.y, xa.y, acc[jj + 1][1]);
-                acc[jj + 1][2] = fma(cc.y, xb.x, acc[jj + 1][2]);
-                acc[jj + 1][3] = fma(cc.y, xb.y, acc[jj + 1][3]);
+                for (int jj = 0; jj < YJ; jj += 2) {
+                    const double2 cc = *reinterpret_cast<const double2*>(&sm.coefs[s][warp][r][jj]);
+                    acc[jj][0] = fma(cc.x, xa.x, acc[jj][0]);
+                    acc[jj][1] = fma(cc.x, xa.y, acc[jj][1]);
+                    acc[jj][2] = fma(cc.x, xb.x, acc[jj][2]);
+                    acc[jj][3] = fma(cc.x, xb.y, acc[jj][3]);
+                    acc[jj + 1][0] = fma(cc.y, xa.x, acc[jj + 1][0]);
+                    acc[jj + 1][1] = fma(cc.y, xa.y, acc[jj + 1][1]);
+                    acc[jj + 1][2] = fma(cc.y, xb.x, acc[jj + 1][2]);
+                    acc[jj + 1][3] = fma(cc.y, xb.y, acc[jj + 1][3]);
+                }
             }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.empty[s]);
     }
+    if (!have) return;
 
     // r_zs interior (df.cpp:377): extended column x -> logical column x + yshift
-    const int xa0 = it.col0 + warp * 128 + 2 * lane;
+    const int xa0 = t.col0 + 2 * lane;
     const bool vec_ok = ((F.zoff + F.yshift) & 1) == 0;   // pitch_z is even, x is even
 #pragma unroll
     for (int jj = 0; jj < YJ; ++jj) {
@@ -264,22 +287,34 @@ __global__ void __launch_bounds__(160) ysweep_tma_kernel(const __grid_constant__
 // =================================================================================================
 // H2z + H3 + H4 + H5 tuned: z-sweep for row-uniform half-widths with the fused epilogue.
 //
-// One CTA = one row j x 1024 columns, all three fields.  Lane l of warp w owns the Z_KC = 8
-// consecutive outputs k = c0 + 256w + 8l + (0..7).  Along z every output of a row shares one
-// coefficient vector, so the tap loop is a register-blocked Toeplitz product: per chunk of 8 samples
-// the thread loads 8 samples (4 LDS.128, stride-10 padded layout -> conflict-free) and 8 new
-// coefficients (4 warp-broadcast LDS.128) and issues 64 DFMA.  The three fields' results stay in
-// registers for the epilogue, which reads filt_old once and writes filt_old, u', v', w', T', rho' once.
+// One CTA = one row j x (128*KC) columns, all three fields.  Lane l of warp w owns the KC consecutive
+// outputs k = c0 + 32*KC*w + KC*l + (0..KC-1).  Along z every output of a row shares one coefficient
+// vector, so the tap loop is a register-blocked Toeplitz product: per chunk of KC samples the thread
+// loads KC samples (LDS.128, stride KC+2 padded layout -> conflict-free) and KC new coefficients
+// (warp-broadcast LDS.128) and issues KC*KC DFMA -- 16 LDS per 256 DFMA at KC = 16.  The row window
+// is staged with 16-byte cp.async straight into the padded layout.  The epilogue runs field by
+// field: filt_old is prefetched before the tap loop, blended (H3), scaled (H4; v' needs u's
+// filtered value, kept in registers), SRA'd (H5), and every output is written exactly once.
 // =================================================================================================
-constexpr int Z_PAD = 10;   // smem doubles per 8 samples
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(valid ? 16 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
 
+template <int KC>
 __global__ void __launch_bounds__(128) zsweep_epilogue_kernel(const ZParams P) {
+    constexpr int PAD = KC + 2;          // smem doubles per KC samples
+    constexpr int TK = 128 * KC;         // columns per CTA
     extern __shared__ __align__(16) double zsm[];
     const PlaneDev& D = P.D;
     const int j = blockIdx.y;
-    const int c0 = blockIdx.x * Z_TK;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int samp_stride = (P.max_len / 8) * Z_PAD;
+    const int c0 = blockIdx.x * TK;
+    const int samp_stride = (P.max_len / KC) * PAD;
     double* s_samp = zsm;                                   // [3][samp_stride]
     double* s_coef = zsm + 3 * samp_stride;                 // [3][max_coef]
 
@@ -289,101 +324,122 @@ __global__ void __launch_bounds__(128) zsweep_epilogue_kernel(const ZParams P) {
         const FieldDev& F = D.f[f];
         const int N = F.Nz_row[j];
         Nf[f] = N;
-        // window element e <-> logical column c0 + Nz_max - N + e, e in [0, Z_TK + 2N + 8)
-        const int len = Z_TK + 8 + ((2 * N + 7) & ~7);   // every chunk the tap loop touches is initialised
+        // window element e <-> logical column c0 + Nz_max - N + e; every chunk the tap loop touches is initialised
+        const int len = TK + KC + ((2 * N + KC - 1) / KC) * KC;
         const int Wz = D.W + 2 * F.Nz_max;
         const int cbase = c0 + F.Nz_max - N;
         const double* src = F.r_zs + (size_t)j * F.pitch_z + F.zoff;
         double* dsts = s_samp + f * samp_stride;
-        for (int e = threadIdx.x; e < len; e += blockDim.x) {
-            const int c = cbase + e;
-            dsts[(e >> 3) * Z_PAD + (e & 7)] = (c < Wz) ? src[c] : 0.0;
+        if (P.async_fill) {
+            for (int e = 2 * threadIdx.x; e < len; e += 2 * blockDim.x) {
+                const int c = cbase + e;
+                cp_async16(&dsts[(e / KC) * PAD + (e % KC)], (c < Wz) ? (src + c) : src, c < Wz);
+            }
+        } else {
+            for (int e = threadIdx.x; e < len; e += blockDim.x) {
+                const int c = cbase + e;
+                dsts[(e / KC) * PAD + (e % KC)] = (c < Wz) ? src[c] : 0.0;
+            }
         }
-        // padded coefficient vector B[m] = b[m - 8 - N] for m-8 in [0, 2N], else 0
+        // padded coefficient vector B[m] = b[m - KC] for m-KC in [0, 2N], else 0
         const double* b = D.coef_vals + D.coef_ptr[N];
         double* dstc = s_coef + f * P.max_coef;
-        const int clen = 2 * N + 32;
+        const int clen = 2 * N + 3 * KC;
         for (int m = threadIdx.x; m < clen; m += blockDim.x) {
-            const int t = m - 8;
-            dstc[m] = (t >= 0 && t <= 2 * N) ? b[t] : 0.0;
+            const int t = m - KC;
+            if (t >= 0 && t <= 2 * N) cp_async8(&dstc[m], b + t);
+            else dstc[m] = 0.0;
         }
     }
+    cp_async_wait_all();
     __syncthreads();
 
-    double z[3][Z_KC];
+    const int k0 = c0 + (int)threadIdx.x * KC;
+    const bool active = k0 < D.W;
+    const double* rc = D.rowc + (size_t)j * ROWC;
+    const size_t base = (size_t)j * D.W + k0;
+    const bool full = (k0 + KC <= D.W) && ((base & 1) == 0);
+    const double rcf[3] = {rc[0], rc[2], rc[3]};
+
+    double uf[KC];                       // u's blended filtered value, needed by v' (df.cpp:437)
 #pragma unroll
     for (int f = 0; f < 3; ++f) {
-        const int nchunk = 1 + (2 * Nf[f] + 7) / 8;           // window = 8 + 2N samples
-        const double* xs = s_samp + f * samp_stride + (warp * 32 + lane) * Z_PAD;
+        double2 fo[KC / 2];
+        if (full && !P.S.first_step) {
+#pragma unroll
+            for (int i = 0; i < KC / 2; ++i) fo[i] = __ldcs(reinterpret_cast<const double2*>(D.f[f].filt_old + base) + i);
+        }
+        const int nchunk = 1 + (2 * Nf[f] + KC - 1) / KC;     // window = KC + 2N samples
+        const double* xs = s_samp + f * samp_stride + threadIdx.x * PAD;
         const double* B = s_coef + f * P.max_coef;
-        double acc[Z_KC];
-        double w[15];
+        double acc[KC];
+        double w[2 * KC - 1];
 #pragma unroll
-        for (int i = 0; i < Z_KC; ++i) acc[i] = 0.0;
+        for (int i = 0; i < KC; ++i) acc[i] = 0.0;
 #pragma unroll
-        for (int i = 0; i < 7; ++i) w[i] = 0.0;
+        for (int i = 0; i < KC - 1; ++i) w[i] = 0.0;
         for (int ch = 0; ch < nchunk; ++ch) {
-            double x[8];
+            double x[KC];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const double2 t = *reinterpret_cast<const double2*>(xs + ch * Z_PAD + 2 * i);
+            for (int i = 0; i < KC / 2; ++i) {
+                const double2 t = *reinterpret_cast<const double2*>(xs + ch * PAD + 2 * i);
                 x[2 * i] = t.x; x[2 * i + 1] = t.y;
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const double2 t = *reinterpret_cast<const double2*>(B + 8 * ch + 8 + 2 * i);
-                w[7 + 2 * i] = t.x; w[8 + 2 * i] = t.y;
+            for (int i = 0; i < KC / 2; ++i) {
+                const double2 t = *reinterpret_cast<const double2*>(B + KC * ch + KC + 2 * i);
+                w[KC - 1 + 2 * i] = t.x; w[KC + 2 * i] = t.y;
             }
-            // out[kk] += x[q] * b[p0 + q - kk - N ...] = x[q] * w[q - kk + 7]
+            // out[kk] += x[q] * b[(KC*ch + q) - kk] = x[q] * w[q - kk + KC - 1]      (df.cpp:397-399)
 #pragma unroll
-            for (int q = 0; q < 8; ++q)
+            for (int q = 0; q < KC; ++q)
 #pragma unroll
-                for (int kk = 0; kk < Z_KC; ++kk) acc[kk] = fma(x[q], w[q - kk + 7], acc[kk]);
+                for (int kk = 0; kk < KC; ++kk) acc[kk] = fma(x[q], w[q - kk + KC - 1], acc[kk]);
 #pragma unroll
-            for (int i = 0; i < 7; ++i) w[i] = w[i + 8];
+            for (int i = 0; i < KC - 1; ++i) w[i] = w[i + KC];
         }
-#pragma unroll
-        for (int i = 0; i < Z_KC; ++i) z[f][i] = acc[i];
-    }
+        if (!active) continue;
 
-    const int k0 = c0 + warp * 256 + lane * Z_KC;
-    if (k0 >= D.W) return;
-    const double* rc = D.rowc + (size_t)j * ROWC;
-    const size_t base = (size_t)j * D.W + k0;
-    const bool full = (k0 + Z_KC <= D.W) && ((base & 1) == 0);
-    if (full) {
+        // ---- epilogue for this field ----
+        double* fold = D.f[f].filt_old + base;
+        double* fluc = D.f[f].fluc + base;
+        if (full) {
 #pragma unroll
-        for (int i = 0; i < Z_KC; i += 2) {
-            const double2 gu = *reinterpret_cast<const double2*>(D.f[0].filt_old + base + i);
-            const double2 gv = *reinterpret_cast<const double2*>(D.f[1].filt_old + base + i);
-            const double2 gw = *reinterpret_cast<const double2*>(D.f[2].filt_old + base + i);
-            EpiOut oa, ob;
-            double ua, va, wa, ub, vb, wb;
-            epilogue_cell(rc, P.S, z[0][i], z[1][i], z[2][i], gu.x, gv.x, gw.x, ua, va, wa, oa);
-            epilogue_cell(rc, P.S, z[0][i + 1], z[1][i + 1], z[2][i + 1], gu.y, gv.y, gw.y, ub, vb, wb, ob);
-            *reinterpret_cast<double2*>(D.f[0].filt_old + base + i) = make_double2(ua, ub);
-            *reinterpret_cast<double2*>(D.f[1].filt_old + base + i) = make_double2(va, vb);
-            *reinterpret_cast<double2*>(D.f[2].filt_old + base + i) = make_double2(wa, wb);
-            *reinterpret_cast<double2*>(D.f[0].fluc + base + i) = make_double2(oa.u, ob.u);
-            *reinterpret_cast<double2*>(D.f[1].fluc + base + i) = make_double2(oa.v, ob.v);
-            *reinterpret_cast<double2*>(D.f[2].fluc + base + i) = make_double2(oa.w, ob.w);
-            if (!P.S.first_step) {
-                *reinterpret_cast<double2*>(D.T_fluc + base + i) = make_double2(oa.T, ob.T);
-                *reinterpret_cast<double2*>(D.rho_fluc + base + i) = make_double2(oa.rho, ob.rho);
+            for (int i = 0; i < KC; i += 2) {
+                double za = acc[i], zb = acc[i + 1];
+                if (!P.S.first_step) {                                   // correlate_fields, df.cpp:415
+                    za = fo[i / 2].x * P.S.sa[f] + za * P.S.sb[f];
+                    zb = fo[i / 2].y * P.S.sa[f] + zb * P.S.sb[f];
+                }
+                *reinterpret_cast<double2*>(fold + i) = make_double2(za, zb);      // filt_old <- filt, df.cpp:440-442
+                double oa = rcf[f] * za, ob = rcf[f] * zb;               // df.cpp:436,438 and the v.filt term of 437
+                if (f == 0) { uf[i] = za; uf[i + 1] = zb; }
+                if (f == 1) { oa = rc[1] * uf[i] + oa; ob = rc[1] * uf[i + 1] + ob; }   // df.cpp:437
+                __stcs(reinterpret_cast<double2*>(fluc + i), make_double2(oa, ob));
+                if (f == 0 && !P.S.first_step) {                         // get_rho_T_fluc, df.cpp:474-481
+                    const double ta = rc[4] * oa, tb = rc[4] * ob;
+                    __stcs(reinterpret_cast<double2*>(D.T_fluc + base + i), make_double2(ta * rc[5], tb * rc[5]));
+                    __stcs(reinterpret_cast<double2*>(D.rho_fluc + base + i), make_double2(-ta * rc[6], -tb * rc[6]));
+                }
             }
-        }
-    } else {
+        } else {
 #pragma unroll
-        for (int i = 0; i < Z_KC; ++i) {
-            if (k0 + i >= D.W) break;
-            const size_t idx = base + i;
-            EpiOut o;
-            double ou, ov, ow;
-            epilogue_cell(rc, P.S, z[0][i], z[1][i], z[2][i], D.f[0].filt_old[idx], D.f[1].filt_old[idx],
-                          D.f[2].filt_old[idx], ou, ov, ow, o);
-            D.f[0].filt_old[idx] = ou; D.f[1].filt_old[idx] = ov; D.f[2].filt_old[idx] = ow;
-            D.f[0].fluc[idx] = o.u; D.f[1].fluc[idx] = o.v; D.f[2].fluc[idx] = o.w;
-            if (!P.S.first_step) { D.T_fluc[idx] = o.T; D.rho_fluc[idx] = o.rho; }
+            for (int i = 0; i < KC; ++i) {
+                if (k0 + i < D.W) {
+                    double za = acc[i];
+                    if (!P.S.first_step) za = fold[i] * P.S.sa[f] + za * P.S.sb[f];
+                    fold[i] = za;
+                    double oa = rcf[f] * za;
+                    if (f == 0) uf[i] = za;
+                    if (f == 1) oa = rc[1] * uf[i] + oa;
+                    fluc[i] = oa;
+                    if (f == 0 && !P.S.first_step) {
+                        const double ta = rc[4] * oa;
+                        D.T_fluc[base + i] = ta * rc[5];
+                        D.rho_fluc[base + i] = -ta * rc[6];
+                    }
+                }
+            }
         }
     }
 }
@@ -430,32 +486,43 @@ cudaError_t launch_zsweep_simple(const PlaneDev& D, const StepConsts& S, cudaStr
     return cudaGetLastError();
 }
 
-constexpr int Y_RC = 8, Y_NS = 3;
+constexpr int Y_RC = 8, Y_NS = 6;
 
 size_t ysweep_smem_bytes() { return sizeof(YSmem<Y_RC, Y_NS>); }
 int ysweep_rc() { return Y_RC; }
 
 cudaError_t ysweep_prepare() {
-    return cudaFuncSetAttribute(ysweep_tma_kernel<Y_RC, Y_NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)sizeof(YSmem<Y_RC, Y_NS>));
+    cudaError_t e = cudaFuncSetAttribute(ysweep_tma_kernel<Y_RC, Y_NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(YSmem<Y_RC, Y_NS>));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(ysweep_tma_kernel<Y_RC, Y_NS>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                cudaSharedmemCarveoutMaxShared);
 }
 
-cudaError_t launch_ysweep_tma(const YMaps& maps, const YParams& P, int n_items, cudaStream_t st) {
-    ysweep_tma_kernel<Y_RC, Y_NS><<<(unsigned)n_items, 160, sizeof(YSmem<Y_RC, Y_NS>), st>>>(maps, P);
+cudaError_t launch_ysweep_tma(const YMaps& maps, const YParams& P, int n_tiles, cudaStream_t st) {
+    ysweep_tma_kernel<Y_RC, Y_NS><<<(unsigned)n_tiles, 160, sizeof(YSmem<Y_RC, Y_NS>), st>>>(maps, P);
     return cudaGetLastError();
 }
 
-size_t zsweep_smem_bytes(int max_len, int max_coef) {
-    return sizeof(double) * (size_t)(3 * (max_len / 8) * Z_PAD + 3 * max_coef);
+int zsweep_kc(int W) { return W >= 1536 ? 16 : 8; }
+
+size_t zsweep_smem_bytes(int kc, int max_len, int max_coef) {
+    return sizeof(double) * (size_t)(3 * (max_len / kc) * (kc + 2) + 3 * max_coef);
 }
 
-cudaError_t zsweep_prepare(size_t smem) {
-    return cudaFuncSetAttribute(zsweep_epilogue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+cudaError_t zsweep_prepare(int kc, size_t smem) {
+    const void* fn = kc == 16 ? (const void*)zsweep_epilogue_kernel<16> : (const void*)zsweep_epilogue_kernel<8>;
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
 cudaError_t launch_zsweep_tuned(const ZParams& P, cudaStream_t st) {
-    dim3 grid((unsigned)((P.D.W + Z_TK - 1) / Z_TK), (unsigned)P.D.Ny);
-    zsweep_epilogue_kernel<<<grid, 128, zsweep_smem_bytes(P.max_len, P.max_coef), st>>>(P);
+    const int tk = 128 * P.kc;
+    dim3 grid((unsigned)((P.D.W + tk - 1) / tk), (unsigned)P.D.Ny);
+    const size_t smem = zsweep_smem_bytes(P.kc, P.max_len, P.max_coef);
+    if (P.kc == 16) zsweep_epilogue_kernel<16><<<grid, 128, smem, st>>>(P);
+    else zsweep_epilogue_kernel<8><<<grid, 128, smem, st>>>(P);
     return cudaGetLastError();
 }
 
