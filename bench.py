@@ -42,50 +42,53 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled DURING the timed region (B200_PROFILING.md): NVML every
+    2 ms from a thread (pynvml ships in the image); nvidia-smi -lms as the fall-back."""
+    REASONS = (("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40),
+               ("hw_power_brake_slowdown", 0x80), ("sw_power_cap", 0x4))
 
     def __init__(self, gpu_index):
-        self.idx, self.p, self.lines = gpu_index, None, []
+        self.idx, self.samples, self.stop_flag, self.t, self.h, self.nv = gpu_index, [], False, None, None, None
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
-                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.idx]) if vis and vis.split(",")[self.idx].isdigit() else self.idx
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
         except Exception:
-            self.p = None
+            self.nv = None
+            return
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
 
-    def _read(self):
-        for ln in self.p.stdout:
-            self.lines.append(ln.strip())
+    def _run(self):
+        nv, h = self.nv, self.h
+        while not self.stop_flag:
+            try:
+                self.samples.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)),
+                                     int(nv.nvmlDeviceGetCurrentClocksEventReasons(h)),
+                                     float(nv.nvmlDeviceGetPowerUsage(h)) / 1e3))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def stop(self):
-        if not self.p:
+        if not self.nv or not self.t:
             return None
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=2)
-        except Exception:
-            self.p.kill()
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
-            c = [x.strip() for x in ln.split(",")]
-            if len(c) < 9:
-                continue
-            try:
-                sm.append(float(c[1])); mx.append(float(c[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
+        self.stop_flag = True
+        self.t.join(timeout=1)
+        if not self.samples:
             return None
-        busy = [s for s in sm if s > 0.5 * max(sm)] or sm
-        return dict(sm_mhz=float(np.median(busy)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        sm = [s[0] for s in self.samples]
+        mask = 0
+        for s in self.samples:
+            mask |= s[1]
+        reasons = [n for n, bit in self.REASONS if mask & bit]
+        return dict(sm_mhz=float(np.median(sm)), sm_min_mhz=float(min(sm)), sm_max_mhz=self.max_mhz, reasons=reasons,
+                    power_w_max=max(s[2] for s in self.samples), samples=len(sm))
 
 
 # --------------------------------------------------------------------------------------------------
@@ -147,8 +150,11 @@ def run_reference_arm(args, plane):
         return
     ncores = os.cpu_count() or 1
     nproc = max(1, min(ncores, 32))
-    s, taps = sample_plane(plane, target_taps=2.0e8)
-    secs, kind = cpu_reference_run(s, args.steps, min(args.warmup, 1), nproc)
+    # bounded sample: ~100 s of wall clock for the whole --steps/--warmup run at ~0.4 G tap/s per core
+    wu = min(args.warmup, 2)
+    target = min(2.0e8, max(1.0e7, 0.4e9 * 100.0 / (args.steps + wu)))
+    s, taps = sample_plane(plane, target_taps=target)
+    secs, kind = cpu_reference_run(s, args.steps, wu, nproc)
     cells = s["Ny"] * s["Nz"] * nproc * args.steps
     value = cells / secs
     line = dict(impl="reference", metric=METRIC, value=value, unit="cell-updates/s", n_gpus=args.gpus, steps=args.steps,
@@ -315,8 +321,8 @@ def run_b200(args, plane):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -217,6 +217,7 @@ class DIGITAL_FILTER:
         _check(L.dfb_dims(self._h, C.byref(ny), C.byref(nz)))
         self.Ny, self.Nz, self.n_cells = ny.value, nz.value, ny.value * nz.value
         self.noise_mode = config.noise_mode
+        self._device = self.info(6)
         self.u, self.v, self.w = (FilterField(self, i) for i in range(3))
         self.T_fluc = np.zeros((self.Ny, self.Nz))
         self.rho_fluc = np.zeros((self.Ny, self.Nz))
@@ -268,6 +269,18 @@ class DIGITAL_FILTER:
         p = C.c_void_p()
         _check(lib().dfb_device_ptr(self._h, which, C.byref(p)))
         return p.value
+
+    def device_tensor(self, which):
+        """zero-copy torch view (Ny, Nz) of a device-resident field (for NCCL hand-offs)"""
+        import torch
+
+        class _View:
+            pass
+
+        v = _View()
+        v.__cuda_array_interface__ = dict(shape=(self.Ny, self.Nz), typestr="<f8", data=(self.device_ptr(which), False),
+                                          version=3, strides=None)
+        return torch.as_tensor(v, device=torch.device("cuda", self._device))
 
     def stream(self):
         p = C.c_void_p()

@@ -481,6 +481,7 @@ int dfb_info(dfb_handle h, int what, int field, int64_t* out64) {
         case 3: *out64 = h->tuned ? 1 : 0; break;
         case 4: *out64 = h->plan.taps_per_step; break;
         case 5: *out64 = h->plan.NzG; break;
+        case 6: *out64 = h->device; break;
         default: return fail(DFB_ERR_ARG, "unknown info selector");
     }
     return DFB_OK;
