@@ -3,6 +3,7 @@
 // There is no CPU fallback: without an sm_100 device dfb_create fails with DFB_ERR_CUDA.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -69,6 +70,7 @@ struct dfb_filter_s {
     int n_items = 0;
     // tuned z-sweep
     ZParams zp[2]{};
+    ZMaps zmaps[2]{};
     // noise
     std::vector<NoiseHost> noise;
     NoiseParams np{};
@@ -245,15 +247,88 @@ void build_device(dfb_filter_s& H) {
         CUDA_TRY(ysweep_prepare());
         ZParams& Z = H.zp[0];
         Z.D = H.D[0];
-        Z.kc = zsweep_kc(W);
-        Z.max_len = 128 * Z.kc + Z.kc + round_up(2 * maxNz, Z.kc);
-        Z.max_coef = 2 * maxNz + 3 * Z.kc;
-        Z.async_fill = 1;   // 16-byte cp.async staging needs every window start on an even column
-        for (int f = 0; f < 3; ++f) {
-            if (P.f[f].Nz_max & 1) Z.async_fill = 0;
-            for (int v : P.f[f].N_z_row) if (v & 1) Z.async_fill = 0;
+        {
+            const int ZKc = zsweep_k(), strip = zsweep_strip();
+            // padded coefficient vectors: the staged window starts on a 128-byte line, d(N) columns before the
+            // first tap (zoff + Nz_max is a multiple of 16 and strips start on multiples of 512, so d = (-N) mod 16)
+            std::vector<long long> pptr(P.coef.Nmax + 1, -1);
+            std::vector<double> pvals;
+            int maxlines = 0, maxcoef = 0;
+            std::vector<char> need(P.coef.Nmax + 1, 0);
+            for (int f = 0; f < 3; ++f) for (int v : P.f[f].N_z_row) need[v] = 1;
+            for (int N = 0; N <= P.coef.Nmax; ++N) {
+                if (!need[N]) continue;
+                const int d = ((-N) % 16 + 16) % 16;
+                const int nchunk = 1 + (2 * N + d + ZKc - 1) / ZKc;
+                const int clen = (nchunk + 1) * ZKc;
+                pptr[N] = (long long)pvals.size();
+                pvals.resize(pvals.size() + clen, 0.0);
+                double* B = pvals.data() + pptr[N];
+                const double* b = P.coef.vals.data() + P.coef.ptr[N];
+                for (int t = 0; t <= 2 * N; ++t) B[t + ZKc + d] = b[t];
+                maxlines = std::max(maxlines, 32 + nchunk);          // lane 31 reads line 31 + ch, ch < nchunk
+                maxcoef = std::max(maxcoef, clen);
+            }
+            Z.coef_pad = H.upload(pvals);
+            Z.coef_pad_ptr = H.upload(pptr);
+            Z.box_lines = maxlines;
+            Z.unit_bytes = round_up(maxlines * 128 + maxcoef * 8, 1024);
+            Z.smem_bytes = 4 * 2 * Z.unit_bytes + 4 * 2 * 8 + 4 * 2 * 64 + 1024;   // buffers, mbarriers, item descriptors, alignment slack
+            if (maxlines > 256) throw Error{DFB_ERR_ARG, "z half-width too large for the staged window (N_z <= 1700)"};
+            // items (row, strip), most expensive first; workers pull them from a counter
+            std::vector<ZItem> items;
+            std::vector<long long> cost;
+            for (int j = 0; j < Ny; ++j) {
+                ZItem it{};
+                it.j = j;
+                long long c = 0;
+                for (int f = 0; f < 3; ++f) {
+                    const int N = P.f[f].N_z_row[j];
+                    const int d = ((-N) % 16 + 16) % 16;
+                    it.nchunk[f] = 1 + (2 * N + d + ZKc - 1) / ZKc;
+                    it.cbytes[f] = (it.nchunk[f] + 1) * ZKc * (int)sizeof(double);
+                    it.coff16[f] = (int)(pptr[N] / 16);
+                    c += 2 * N + 48;
+                }
+                for (int c0 = 0; c0 < W; c0 += strip) {
+                    it.c0 = c0;
+                    for (int f = 0; f < 3; ++f) {
+                        const FieldDev& F = H.D[0].f[f];
+                        const int s0 = F.zoff + c0 + F.Nz_max - P.f[f].N_z_row[j];   // storage column of output c0's first tap
+                        it.line0[f] = s0 >> 4;                                       // (s0 & 15) == d by construction
+                    }
+                    items.push_back(it); cost.push_back(c);
+                }
+            }
+            std::vector<int> order(items.size());
+            for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+            std::stable_sort(order.begin(), order.end(), [&](int a, int b2) { return cost[a] > cost[b2]; });
+            std::vector<ZItem> sorted(items.size());
+            for (size_t i = 0; i < order.size(); ++i) sorted[i] = items[order[i]];
+            Z.items = H.upload(sorted);
+            Z.n_items = (int)sorted.size();
+            Z.counter = H.dalloc<int>(1);
+            Z.debug = std::getenv("DFB_DEBUG_Z") ? std::atoi(std::getenv("DFB_DEBUG_Z")) : 0;
+            cudaDeviceProp prop;
+            CUDA_TRY(cudaGetDeviceProperties(&prop, H.device));
+            const int zb = std::getenv("DFB_Z_BLOCKS_PER_SM") ? std::atoi(std::getenv("DFB_Z_BLOCKS_PER_SM")) : 2;
+            Z.nblocks = std::max(1, std::min(zb * prop.multiProcessorCount, (Z.n_items + 3) / 4));
+            CUDA_TRY(zsweep_prepare((size_t)Z.smem_bytes));
+            H.yp[0].zcounter = Z.counter;
+            H.yp[1].zcounter = Z.counter;
+            for (int b = 0; b < 2; ++b)
+                for (int f = 0; f < 3; ++f) {
+                    const FieldDev& F = H.D[b].f[f];
+                    cuuint64_t dims[3] = {16, (cuuint64_t)(F.pitch_z / 16), (cuuint64_t)Ny};
+                    cuuint64_t strides[2] = {128, (cuuint64_t)F.pitch_z * sizeof(double)};
+                    cuuint32_t box[3] = {16u, (cuuint32_t)Z.box_lines, 1u};
+                    cuuint32_t estr[3] = {1u, 1u, 1u};
+                    CUresult r = encode_tiled()(&H.zmaps[b].m[f], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, F.r_zs, dims, strides, box, estr,
+                                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    if (r != CUDA_SUCCESS) throw Error{DFB_ERR_CUDA, "cuTensorMapEncodeTiled (z) failed (" + std::to_string((int)r) + ")"};
+                }
         }
-        CUDA_TRY(zsweep_prepare(Z.kc, zsweep_smem_bytes(Z.kc, Z.max_len, Z.max_coef)));
         H.zp[1] = Z;
         H.zp[1].D = H.D[1];
         
@@ -350,7 +425,7 @@ void run_step(dfb_filter_s& H, double dt, bool first) {
         S.sa[f] = std::sqrt(alpha);                                // df.cpp:415
         S.sb[f] = std::sqrt(1.0 - alpha);
     }
-    if (H.tuned) { H.zp[b].S = S; CUDA_TRY(launch_zsweep_tuned(H.zp[b], H.stream)); }
+    if (H.tuned) { H.zp[b].S = S; CUDA_TRY(launch_zsweep_tuned(H.zmaps[b], H.zp[b], H.stream)); }
     else CUDA_TRY(launch_zsweep_simple(H.D[b], S, H.stream));
     CUDA_TRY(cudaEventRecord(H.ev_free[b], H.stream));
     if (H.timing) CUDA_TRY(cudaEventRecord(H.ev[3], H.stream));

@@ -97,16 +97,34 @@ struct YParams {
     const YGroup* groups;
     const YTile* tiles;
     const double* cmat;
+    int* zcounter;             // work counter of the z-sweep that follows (reset here)
     PlaneDev D;
 };
+
+struct ZItem {                     // one row x one strip of 512 columns: 16 ints, everything a unit needs precomputed
+    int j, c0;
+    int nchunk[3];                 // tap-loop chunks per field
+    int line0[3];                  // first 128-byte line of the staged window per field
+    int cbytes[3];                 // bytes of the padded coefficient vector per field
+    int coff16[3];                 // offset of the padded coefficient vector in coef_pad, in units of 16 doubles
+    int pad_[2];
+};
+static_assert(sizeof(ZItem) == 64, "ZItem is loaded as 16 ints, one per lane");
+struct ZMaps { CUtensorMap m[3]; };   // r_zs[f] as {16 doubles, pitch/16 lines, Ny rows}, 128-byte swizzle
 
 struct ZParams {
     PlaneDev D;
     StepConsts S;
-    int kc;             // consecutive outputs per thread: 16 (wide planes) or 8; the CTA covers 128*kc columns
-    int max_len;        // samples per field window in smem: 128*kc + kc + round_up(2*max(Nz_max), kc)
-    int max_coef;       // coefficient slots per field: 2*max(Nz_max) + 3*kc
-    int async_fill;     // 1: every N_z is even -> 16-byte cp.async staging; 0: scalar staging
+    const ZItem* items;          // most expensive first
+    int n_items;
+    int* counter;                // work counter, zeroed by the y-sweep that precedes this launch
+    const double* coef_pad;      // padded coefficient vectors B_N[m] = b_N[m - 16 - d(N)], zero elsewhere
+    const long long* coef_pad_ptr;   // [Nmax+1] offsets (doubles, 16-byte aligned) into coef_pad
+    int box_lines;               // 128-byte lines per staged window (box height of the tensor maps)
+    int unit_bytes;              // bytes per staging buffer: box_lines*128 + padded coefficient vector, 1024-aligned
+    int nblocks;
+    int smem_bytes;
+    int debug;                   // development probes only (0 in production)
 };
 
 }  // namespace dfb

@@ -194,6 +194,7 @@ __global__ void __launch_bounds__(160, 3) ysweep_tma_kernel(const __grid_constan
     if (threadIdx.x == 0) {
         for (int s = 0; s < NS; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], Y_G); }
         mbar_fence_init();
+        if (blockIdx.x == 0 && P.zcounter) *P.zcounter = 0;      // the z-sweep that follows pulls its items from here
     }
     __syncthreads();
 
@@ -287,160 +288,272 @@ __global__ void __launch_bounds__(160, 3) ysweep_tma_kernel(const __grid_constan
 // =================================================================================================
 // H2z + H3 + H4 + H5 tuned: z-sweep for row-uniform half-widths with the fused epilogue.
 //
-// One CTA = one row j x (128*KC) columns, all three fields.  Lane l of warp w owns the KC consecutive
-// outputs k = c0 + 32*KC*w + KC*l + (0..KC-1).  Along z every output of a row shares one coefficient
-// vector, so the tap loop is a register-blocked Toeplitz product: per chunk of KC samples the thread
-// loads KC samples (LDS.128, stride KC+2 padded layout -> conflict-free) and KC new coefficients
-// (warp-broadcast LDS.128) and issues KC*KC DFMA -- 16 LDS per 256 DFMA at KC = 16.  The row window
-// is staged with 16-byte cp.async straight into the padded layout.  The epilogue runs field by
-// field: filt_old is prefetched before the tap loop, blended (H3), scaled (H4; v' needs u's
-// filtered value, kept in registers), SRA'd (H5), and every output is written exactly once.
+// Persistent and warp-independent: every warp is a worker that pulls items (row j, strip of 512
+// columns; most expensive first) from a global counter and runs each item field by field (u, v, w)
+// through a private double-buffered shared-memory window.  One unit = (item, field):
+//   * staging: ONE lane issues two TMA operations per unit -- a 3-D cp.async.bulk.tensor box
+//     {16 doubles, 50 x 128-byte lines, 1 row} of r_zs with 128-byte swizzle (lane l's 16 samples of
+//     chunk ch are line l+ch; the swizzle makes the LDS.128 of 8 consecutive lines conflict-free)
+//     and a cp.async.bulk of the row's padded coefficient vector -- both landing on the unit's
+//     mbarrier while the previous unit is still in its tap loop;
+//   * tap loop: lane l owns the 16 consecutive outputs k = c0 + 16 l + (0..15).  Along z every
+//     output of a row shares one coefficient vector, so the loop is a register-blocked Toeplitz
+//     product: per chunk 16 samples + 16 new coefficients (16 LDS.128) feed 256 DFMA.  The window
+//     starts on a 128-byte line; the distance d to the first tap is folded into the padded vector
+//     B[m] = b[m - 16 - d];
+//   * epilogue per field from registers: filt_old prefetched before the tap loop, blend (H3),
+//     Lund scaling (H4; v' uses u's blended value kept in registers), SRA (H5); each of the eight
+//     output arrays is written exactly once with streaming stores.
 // =================================================================================================
-__device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(valid ? 16 : 0) : "memory");
-}
-__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+// Cell arithmetic of the fused epilogue with every rounding spelled out, so that the result does not
+// depend on which code path (coalesced / direct / partial strip) a cell takes: slabs stay bit-identical
+// to the whole plane.
+__device__ __forceinline__ double epi_blend(double fo, double sa, double z, double sb) { return __fma_rn(fo, sa, __dmul_rn(z, sb)); }
+__device__ __forceinline__ double epi_scale(double rc, double z) { return __dmul_rn(rc, z); }
+__device__ __forceinline__ double epi_cross(double rc1, double uf, double o) { return __fma_rn(rc1, uf, o); }
+
+constexpr int ZK = 16;                 // outputs per lane
+constexpr int Z_STRIP = 32 * ZK;       // columns per item
+
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
 }
 
-template <int KC>
-__global__ void __launch_bounds__(128) zsweep_epilogue_kernel(const ZParams P) {
-    constexpr int PAD = KC + 2;          // smem doubles per KC samples
-    constexpr int TK = 128 * KC;         // columns per CTA
-    extern __shared__ __align__(16) double zsm[];
+__device__ __forceinline__ void z_issue_unit(const ZParams& P, const ZMaps& maps, const int* desc, int f, void* buf, uint64_t* bar) {
+    // called by one lane: two TMA operations land the unit's window and coefficient vector on `bar`.
+    // The buffer was last touched through the generic proxy (tap-loop reads, transpose scratch):
+    // order those accesses before the async-proxy writes of the TMA engine.
+    // desc = ZItem as 16 ints in shared memory: [0] j, [1] c0, [2..4] nchunk, [5..7] line0, [8..10] cbytes, [11..13] coff16
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    const uint32_t cbytes = (uint32_t)desc[8 + f];
+    mbar_expect_tx(bar, (uint32_t)(P.box_lines * 128) + cbytes);
+    tma_load_3d(buf, &maps.m[f], 0, desc[5 + f], desc[0], bar);
+    tma_load_1d(reinterpret_cast<unsigned char*>(buf) + P.box_lines * 128, P.coef_pad + (size_t)desc[11 + f] * 16, cbytes, bar);
+}
+
+__global__ void __launch_bounds__(128) zsweep_epilogue_kernel(const __grid_constant__ ZMaps maps, const ZParams P) {
+    extern __shared__ __align__(1024) unsigned char zsm_unaligned[];
+    // the 128-byte swizzle is a function of the shared-memory address: put the buffers on a 1 KiB boundary
+    unsigned char* zsm_raw = zsm_unaligned + ((1024u - (smem_u32(zsm_unaligned) & 1023u)) & 1023u);
     const PlaneDev& D = P.D;
-    const int j = blockIdx.y;
-    const int c0 = blockIdx.x * TK;
-    const int samp_stride = (P.max_len / KC) * PAD;
-    double* s_samp = zsm;                                   // [3][samp_stride]
-    double* s_coef = zsm + 3 * samp_stride;                 // [3][max_coef]
+    // Warp index through a shuffle: the compiler then knows every address derived from it is warp-uniform and
+    // keeps the (warp-broadcast) coefficients in uniform registers -- DFMA R, R.reuse, UR, R needs one fresh
+    // vector-register operand instead of two and runs at the fp64 pipe's full rate.  (For the same reason the
+    // field loop below must NOT be unrolled and the kernel carries no minBlocksPerSM hint: either makes ptxas
+    // fall back to vector registers for the coefficients, at ~70 % of the rate.)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    // per warp: 2 buffers of unit_bytes (window lines + coefficient vector); then 2 mbarriers and 2 item descriptors per warp
+    unsigned char* wbase = zsm_raw + (size_t)warp * 2 * P.unit_bytes;
+    unsigned char* tail = zsm_raw + (size_t)4 * 2 * P.unit_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tail) + warp * 2;
+    int* descs = reinterpret_cast<int*>(tail + 64) + warp * 32;              // [2][16]
+    if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
 
-    int Nf[3];
-#pragma unroll
-    for (int f = 0; f < 3; ++f) {
-        const FieldDev& F = D.f[f];
-        const int N = F.Nz_row[j];
-        Nf[f] = N;
-        // window element e <-> logical column c0 + Nz_max - N + e; every chunk the tap loop touches is initialised
-        const int len = TK + KC + ((2 * N + KC - 1) / KC) * KC;
-        const int Wz = D.W + 2 * F.Nz_max;
-        const int cbase = c0 + F.Nz_max - N;
-        const double* src = F.r_zs + (size_t)j * F.pitch_z + F.zoff;
-        double* dsts = s_samp + f * samp_stride;
-        if (P.async_fill) {
-            for (int e = 2 * threadIdx.x; e < len; e += 2 * blockDim.x) {
-                const int c = cbase + e;
-                cp_async16(&dsts[(e / KC) * PAD + (e % KC)], (c < Wz) ? (src + c) : src, c < Wz);
-            }
-        } else {
-            for (int e = threadIdx.x; e < len; e += blockDim.x) {
-                const int c = cbase + e;
-                dsts[(e / KC) * PAD + (e % KC)] = (c < Wz) ? src[c] : 0.0;
-            }
-        }
-        // padded coefficient vector B[m] = b[m - KC] for m-KC in [0, 2N], else 0
-        const double* b = D.coef_vals + D.coef_ptr[N];
-        double* dstc = s_coef + f * P.max_coef;
-        const int clen = 2 * N + 3 * KC;
-        for (int m = threadIdx.x; m < clen; m += blockDim.x) {
-            const int t = m - KC;
-            if (t >= 0 && t <= 2 * N) cp_async8(&dstc[m], b + t);
-            else dstc[m] = 0.0;
-        }
-    }
-    cp_async_wait_all();
-    __syncthreads();
+    int claim = 0;
+    if (lane == 0) claim = atomicAdd(P.counter, 1);
+    int item = __shfl_sync(0xffffffffu, claim, 0);
+    if (item >= P.n_items) return;
+    if (lane < 16) descs[lane] = reinterpret_cast<const int*>(P.items + item)[lane];
+    __syncwarp();
+    if (lane == 0) z_issue_unit(P, maps, descs, 0, wbase, &bars[0]);
 
-    const int k0 = c0 + (int)threadIdx.x * KC;
-    const bool active = k0 < D.W;
-    const double* rc = D.rowc + (size_t)j * ROWC;
-    const size_t base = (size_t)j * D.W + k0;
-    const bool full = (k0 + KC <= D.W) && ((base & 1) == 0);
-    const double rcf[3] = {rc[0], rc[2], rc[3]};
+    double uf[ZK];                       // u's blended filtered value, needed by v' (df.cpp:437)
+    int n = 0;                           // running unit index: buffer n & 1, barrier phase (n >> 1) & 1
+    for (int k = 0;; ++k) {              // k-th item of this warp; its descriptor lives in descs[(k & 1) * 16 ..]
+        const int* dcur = descs + (k & 1) * 16;
+        int* dnext = descs + ((k + 1) & 1) * 16;
+        const int j = dcur[0], c0 = dcur[1];
+        const int k0 = c0 + lane * ZK;
+        const bool active = k0 < D.W;
+        const size_t base = (size_t)j * D.W + k0;
+        const size_t sbase = (size_t)j * D.W + c0;                            // first cell of the warp's strip
+        const bool full = (k0 + ZK <= D.W) && ((base & 1) == 0);
+        // whole strip inside the plane and 16-byte aligned: go through the shared-memory transpose (coalesced global access)
+        const bool coalesced = (c0 + Z_STRIP <= D.W) && ((sbase & 1) == 0) && !(P.debug & 4);
+        const double* rcp = D.rowc + (size_t)j * ROWC;
+        const double rc1 = __ldg(rcp + 1), rc4 = __ldg(rcp + 4), rc5 = __ldg(rcp + 5), rc6 = __ldg(rcp + 6);
+        int next_item = 0, dreg = 0;
+        bool have_next = false;
 
-    double uf[KC];                       // u's blended filtered value, needed by v' (df.cpp:437)
-#pragma unroll
-    for (int f = 0; f < 3; ++f) {
-        double2 fo[KC / 2];
-        if (full && !P.S.first_step) {
-#pragma unroll
-            for (int i = 0; i < KC / 2; ++i) fo[i] = __ldcs(reinterpret_cast<const double2*>(D.f[f].filt_old + base) + i);
-        }
-        const int nchunk = 1 + (2 * Nf[f] + KC - 1) / KC;     // window = KC + 2N samples
-        const double* xs = s_samp + f * samp_stride + threadIdx.x * PAD;
-        const double* B = s_coef + f * P.max_coef;
-        double acc[KC];
-        double w[2 * KC - 1];
-#pragma unroll
-        for (int i = 0; i < KC; ++i) acc[i] = 0.0;
-#pragma unroll
-        for (int i = 0; i < KC - 1; ++i) w[i] = 0.0;
-        for (int ch = 0; ch < nchunk; ++ch) {
-            double x[KC];
-#pragma unroll
-            for (int i = 0; i < KC / 2; ++i) {
-                const double2 t = *reinterpret_cast<const double2*>(xs + ch * PAD + 2 * i);
-                x[2 * i] = t.x; x[2 * i + 1] = t.y;
+#pragma unroll 1
+        for (int f = 0; f < 3; ++f, ++n) {
+            // ---- work-list look-ahead, spread over the item's three units so no latency is exposed ----
+            if (f == 0) {
+                if (lane == 0) claim = atomicAdd(P.counter, 1);              // claim the next item
+            } else if (f == 1) {
+                next_item = __shfl_sync(0xffffffffu, claim, 0);
+                have_next = next_item < P.n_items;
+                if (have_next && lane < 16) dreg = __ldg(reinterpret_cast<const int*>(P.items + next_item) + lane);
+            } else {
+                if (have_next && lane < 16) dnext[lane] = dreg;
+                __syncwarp();
             }
-#pragma unroll
-            for (int i = 0; i < KC / 2; ++i) {
-                const double2 t = *reinterpret_cast<const double2*>(B + KC * ch + KC + 2 * i);
-                w[KC - 1 + 2 * i] = t.x; w[KC + 2 * i] = t.y;
+            // ---- stage the next unit while this one computes ----
+            const bool more = (f < 2) || have_next;
+            if (more && lane == 0) {
+                unsigned char* nb = wbase + (size_t)((n + 1) & 1) * P.unit_bytes;
+                if (f < 2) z_issue_unit(P, maps, dcur, f + 1, nb, &bars[(n + 1) & 1]);
+                else z_issue_unit(P, maps, dnext, 0, nb, &bars[(n + 1) & 1]);
             }
-            // out[kk] += x[q] * b[(KC*ch + q) - kk] = x[q] * w[q - kk + KC - 1]      (df.cpp:397-399)
-#pragma unroll
-            for (int q = 0; q < KC; ++q)
-#pragma unroll
-                for (int kk = 0; kk < KC; ++kk) acc[kk] = fma(x[q], w[q - kk + KC - 1], acc[kk]);
-#pragma unroll
-            for (int i = 0; i < KC - 1; ++i) w[i] = w[i + KC];
-        }
-        if (!active) continue;
+            const FieldDev& F = D.f[f];
+            const int nchunk = __shfl_sync(0xffffffffu, dcur[2 + f], 0);     // provably uniform trip count (see `warp` above)
+            const double rc_own = __ldg(rcp + (f == 0 ? 0 : (f == 1 ? 2 : 3)));
+            const bool blend = !P.S.first_step;
 
-        // ---- epilogue for this field ----
-        double* fold = D.f[f].filt_old + base;
-        double* fluc = D.f[f].fluc + base;
-        if (full) {
+            // filt_old of this field: requested before the tap loop, consumed after it
+            double2 fo[ZK / 2];
+            if (blend && !(P.debug & 1)) {
+                if (coalesced) {
 #pragma unroll
-            for (int i = 0; i < KC; i += 2) {
-                double za = acc[i], zb = acc[i + 1];
-                if (!P.S.first_step) {                                   // correlate_fields, df.cpp:415
-                    za = fo[i / 2].x * P.S.sa[f] + za * P.S.sb[f];
-                    zb = fo[i / 2].y * P.S.sa[f] + zb * P.S.sb[f];
-                }
-                *reinterpret_cast<double2*>(fold + i) = make_double2(za, zb);      // filt_old <- filt, df.cpp:440-442
-                double oa = rcf[f] * za, ob = rcf[f] * zb;               // df.cpp:436,438 and the v.filt term of 437
-                if (f == 0) { uf[i] = za; uf[i + 1] = zb; }
-                if (f == 1) { oa = rc[1] * uf[i] + oa; ob = rc[1] * uf[i + 1] + ob; }   // df.cpp:437
-                __stcs(reinterpret_cast<double2*>(fluc + i), make_double2(oa, ob));
-                if (f == 0 && !P.S.first_step) {                         // get_rho_T_fluc, df.cpp:474-481
-                    const double ta = rc[4] * oa, tb = rc[4] * ob;
-                    __stcs(reinterpret_cast<double2*>(D.T_fluc + base + i), make_double2(ta * rc[5], tb * rc[5]));
-                    __stcs(reinterpret_cast<double2*>(D.rho_fluc + base + i), make_double2(-ta * rc[6], -tb * rc[6]));
+                    for (int m = 0; m < ZK / 2; ++m)       // piece p = lane + 32 m of the strip: 512 contiguous bytes per instruction
+                        fo[m] = __ldcs(reinterpret_cast<const double2*>(F.filt_old + sbase) + lane + 32 * m);
+                } else if (full) {
+#pragma unroll
+                    for (int i = 0; i < ZK / 2; ++i) fo[i] = __ldcs(reinterpret_cast<const double2*>(F.filt_old + base) + i);
                 }
             }
-        } else {
+
+            mbar_wait(&bars[n & 1], (n >> 1) & 1);
+            unsigned char* cbuf = wbase + (size_t)(n & 1) * P.unit_bytes;
+            // (address through a shuffle: provably warp-uniform -> coefficients in uniform registers)
+            const double* B = reinterpret_cast<const double*>(__cvta_shared_to_generic(
+                (size_t)__shfl_sync(0xffffffffu, smem_u32(cbuf + P.box_lines * 128), 0)));
+            double acc[ZK];
+            double w[2 * ZK - 1];
 #pragma unroll
-            for (int i = 0; i < KC; ++i) {
-                if (k0 + i < D.W) {
-                    double za = acc[i];
-                    if (!P.S.first_step) za = fold[i] * P.S.sa[f] + za * P.S.sb[f];
-                    fold[i] = za;
-                    double oa = rcf[f] * za;
-                    if (f == 0) uf[i] = za;
-                    if (f == 1) oa = rc[1] * uf[i] + oa;
-                    fluc[i] = oa;
-                    if (f == 0 && !P.S.first_step) {
-                        const double ta = rc[4] * oa;
-                        D.T_fluc[base + i] = ta * rc[5];
-                        D.rho_fluc[base + i] = -ta * rc[6];
+            for (int i = 0; i < ZK; ++i) acc[i] = 0.0;
+#pragma unroll
+            for (int i = 0; i < ZK - 1; ++i) w[i] = 0.0;
+            for (int ch = 0; ch < nchunk; ++ch) {
+                const int line = lane + ch;
+                const unsigned char* lp = cbuf + line * 128;
+                const int sw = (line & 7) << 4;          // 128-byte swizzle: 16-byte piece i lives at i ^ (line & 7)
+                double x[ZK];
+#pragma unroll
+                for (int i = 0; i < ZK / 2; ++i) {
+                    const double2 t = *reinterpret_cast<const double2*>(lp + ((i << 4) ^ sw));
+                    x[2 * i] = t.x; x[2 * i + 1] = t.y;
+                }
+#pragma unroll
+                for (int i = 0; i < ZK / 2; ++i) {
+                    const double2 t = *reinterpret_cast<const double2*>(B + ZK * ch + ZK + 2 * i);
+                    w[ZK - 1 + 2 * i] = t.x; w[ZK + 2 * i] = t.y;
+                }
+                // out[kk] += x[q] * b[(16 ch + q) - kk - d] = x[q] * w[q - kk + 15]      (df.cpp:397-399)
+#pragma unroll
+                for (int q = 0; q < ZK; ++q)
+#pragma unroll
+                    for (int kk = 0; kk < ZK; ++kk) acc[kk] = fma(x[q], w[q - kk + ZK - 1], acc[kk]);
+#pragma unroll
+                for (int i = 0; i < ZK - 1; ++i) w[i] = w[i + ZK];
+            }
+            __syncwarp();                // every lane is done with this buffer's window: it becomes the transpose scratch
+
+            if (!((P.debug & 2) && acc[0] != 123.456)) {
+                // ---- epilogue for this field ----
+                const double sa = P.S.sa[f], sb = P.S.sb[f];
+                if (coalesced) {
+                    // Lane l owns line l (its 16 cells) of a 32 x 128-byte scratch tile; global memory wants piece
+                    // p = lane + 32 m.  Both views are conflict-free under the same XOR swizzle.
+                    const int own = lane * 128, osw = (lane & 7) << 4;
+                    auto put_pieces = [&](const double2* v) {      // piece-major registers -> tile
+#pragma unroll
+                        for (int m = 0; m < ZK / 2; ++m) {
+                            const int r = (lane >> 3) + 4 * m;
+                            *reinterpret_cast<double2*>(cbuf + r * 128 + ((((lane & 7) ^ (r & 7))) << 4)) = v[m];
+                        }
+                    };
+                    auto get_pieces = [&](double2* v) {            // tile -> piece-major registers
+#pragma unroll
+                        for (int m = 0; m < ZK / 2; ++m) {
+                            const int r = (lane >> 3) + 4 * m;
+                            v[m] = *reinterpret_cast<const double2*>(cbuf + r * 128 + ((((lane & 7) ^ (r & 7))) << 4));
+                        }
+                    };
+                    auto put_own = [&](const double* v) {          // this lane's 16 cells -> its line
+#pragma unroll
+                        for (int i = 0; i < ZK / 2; ++i)
+                            *reinterpret_cast<double2*>(cbuf + own + ((i << 4) ^ osw)) = make_double2(v[2 * i], v[2 * i + 1]);
+                    };
+                    auto get_own = [&](double* v) {
+#pragma unroll
+                        for (int i = 0; i < ZK / 2; ++i) {
+                            const double2 t = *reinterpret_cast<const double2*>(cbuf + own + ((i << 4) ^ osw));
+                            v[2 * i] = t.x; v[2 * i + 1] = t.y;
+                        }
+                    };
+                    auto store_strip = [&](double* gstrip, const double* v, bool streaming) {
+                        double2 pc[ZK / 2];
+                        put_own(v);
+                        __syncwarp();
+                        get_pieces(pc);
+                        __syncwarp();
+#pragma unroll
+                        for (int m = 0; m < ZK / 2; ++m) {
+                            double2* dst = reinterpret_cast<double2*>(gstrip) + lane + 32 * m;
+                            if (streaming) __stcs(dst, pc[m]); else *dst = pc[m];
+                        }
+                    };
+                    double z[ZK];
+                    if (blend) {
+                        double own_fo[ZK];
+                        put_pieces(fo);
+                        __syncwarp();
+                        get_own(own_fo);
+                        __syncwarp();
+#pragma unroll
+                        for (int i = 0; i < ZK; ++i) z[i] = epi_blend(own_fo[i], sa, acc[i], sb);      // correlate_fields, df.cpp:415
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < ZK; ++i) z[i] = acc[i];
+                    }
+                    store_strip(F.filt_old + sbase, z, false);                                  // filt_old <- filt, df.cpp:440-442
+                    double o[ZK];
+#pragma unroll
+                    for (int i = 0; i < ZK; ++i) {
+                        o[i] = epi_scale(rc_own, z[i]);                                         // df.cpp:436,438; v.filt term of 437
+                        if (f == 0) uf[i] = z[i];
+                        if (f == 1) o[i] = epi_cross(rc1, uf[i], o[i]);                         // df.cpp:437
+                    }
+                    store_strip(F.fluc + sbase, o, true);
+                    if (f == 0 && blend) {                                                      // get_rho_T_fluc, df.cpp:474-481
+                        double t[ZK];
+#pragma unroll
+                        for (int i = 0; i < ZK; ++i) { z[i] = __dmul_rn(rc4, o[i]); t[i] = __dmul_rn(z[i], rc5); }
+                        store_strip(D.T_fluc + sbase, t, true);
+#pragma unroll
+                        for (int i = 0; i < ZK; ++i) t[i] = __dmul_rn(-z[i], rc6);
+                        store_strip(D.rho_fluc + sbase, t, true);
+                    }
+                } else if (active) {
+                    double* __restrict__ fold = F.filt_old + base;
+                    double* __restrict__ fluc = F.fluc + base;
+                    double* __restrict__ Tp = D.T_fluc + base;
+                    double* __restrict__ Rp = D.rho_fluc + base;
+#pragma unroll
+                    for (int i = 0; i < ZK; ++i) {
+                        if (k0 + i < D.W) {
+                            double za = acc[i];
+                            if (blend) za = epi_blend(full ? (i & 1 ? fo[i / 2].y : fo[i / 2].x) : fold[i], sa, za, sb);
+                            fold[i] = za;
+                            double oa = epi_scale(rc_own, za);
+                            if (f == 0) uf[i] = za;
+                            if (f == 1) oa = epi_cross(rc1, uf[i], oa);
+                            fluc[i] = oa;
+                            if (f == 0 && blend) {
+                                const double ta = __dmul_rn(rc4, oa);
+                                Tp[i] = __dmul_rn(ta, rc5);
+                                Rp[i] = __dmul_rn(-ta, rc6);
+                            }
+                        }
                     }
                 }
+                __syncwarp();            // scratch reads are done before the buffer is refilled by the next-but-one unit
             }
         }
+        if (!have_next) break;
     }
 }
 
@@ -504,25 +617,17 @@ cudaError_t launch_ysweep_tma(const YMaps& maps, const YParams& P, int n_tiles, 
     return cudaGetLastError();
 }
 
-int zsweep_kc(int W) { return W >= 1536 ? 16 : 8; }
+int zsweep_strip() { return Z_STRIP; }
+int zsweep_k() { return ZK; }
 
-size_t zsweep_smem_bytes(int kc, int max_len, int max_coef) {
-    return sizeof(double) * (size_t)(3 * (max_len / kc) * (kc + 2) + 3 * max_coef);
-}
-
-cudaError_t zsweep_prepare(int kc, size_t smem) {
-    const void* fn = kc == 16 ? (const void*)zsweep_epilogue_kernel<16> : (const void*)zsweep_epilogue_kernel<8>;
-    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+cudaError_t zsweep_prepare(size_t smem) {
+    cudaError_t e = cudaFuncSetAttribute(zsweep_epilogue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    return cudaFuncSetAttribute(zsweep_epilogue_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
-cudaError_t launch_zsweep_tuned(const ZParams& P, cudaStream_t st) {
-    const int tk = 128 * P.kc;
-    dim3 grid((unsigned)((P.D.W + tk - 1) / tk), (unsigned)P.D.Ny);
-    const size_t smem = zsweep_smem_bytes(P.kc, P.max_len, P.max_coef);
-    if (P.kc == 16) zsweep_epilogue_kernel<16><<<grid, 128, smem, st>>>(P);
-    else zsweep_epilogue_kernel<8><<<grid, 128, smem, st>>>(P);
+cudaError_t launch_zsweep_tuned(const ZMaps& maps, const ZParams& P, cudaStream_t st) {
+    zsweep_epilogue_kernel<<<(unsigned)P.nblocks, 128, P.smem_bytes, st>>>(maps, P);
     return cudaGetLastError();
 }
 

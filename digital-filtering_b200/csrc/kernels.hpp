@@ -11,10 +11,10 @@ size_t ysweep_smem_bytes();
 int ysweep_rc();
 cudaError_t ysweep_prepare();
 cudaError_t launch_ysweep_tma(const YMaps& maps, const YParams& P, int n_items, cudaStream_t st);
-int zsweep_kc(int W);
-size_t zsweep_smem_bytes(int kc, int max_len, int max_coef);
-cudaError_t zsweep_prepare(int kc, size_t smem);
-cudaError_t launch_zsweep_tuned(const ZParams& P, cudaStream_t st);
+int zsweep_strip();
+int zsweep_k();
+cudaError_t zsweep_prepare(size_t smem);
+cudaError_t launch_zsweep_tuned(const ZMaps& maps, const ZParams& P, cudaStream_t st);
 cudaError_t launch_dfma_peak(double* out, int blocks, int iters, cudaStream_t st);
 
 }  // namespace dfb
