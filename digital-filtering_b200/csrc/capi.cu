@@ -248,9 +248,14 @@ void build_device(dfb_filter_s& H) {
         ZParams& Z = H.zp[0];
         Z.D = H.D[0];
         {
-            const int ZKc = zsweep_k(), strip = zsweep_strip();
-            // padded coefficient vectors: the staged window starts on a 128-byte line, d(N) columns before the
-            // first tap (zoff + Nz_max is a multiple of 16 and strips start on multiples of 512, so d = (-N) mod 16)
+            // outputs per lane: 16 (fewest LDS per DFMA) unless the plane is narrower than one 512-column strip
+            const char* zk_env = std::getenv("DFB_ZK");
+            const int ZKc = zk_env ? std::atoi(zk_env) : (W >= 384 ? 16 : 8);
+            if (ZKc != 8 && ZKc != 16) throw Error{DFB_ERR_ARG, "DFB_ZK must be 8 or 16"};
+            const int strip = 32 * ZKc;
+            Z.zk = ZKc;
+            // padded coefficient vectors: the staged window starts on a line boundary, d(N) columns before the first tap
+            // (zoff + Nz_max is a multiple of 16 and strips start on multiples of 32*zk, so d = (-N) mod zk)
             std::vector<long long> pptr(P.coef.Nmax + 1, -1);
             std::vector<double> pvals;
             int maxlines = 0, maxcoef = 0;
@@ -258,9 +263,9 @@ void build_device(dfb_filter_s& H) {
             for (int f = 0; f < 3; ++f) for (int v : P.f[f].N_z_row) need[v] = 1;
             for (int N = 0; N <= P.coef.Nmax; ++N) {
                 if (!need[N]) continue;
-                const int d = ((-N) % 16 + 16) % 16;
+                const int d = ((-N) % ZKc + ZKc) % ZKc;
                 const int nchunk = 1 + (2 * N + d + ZKc - 1) / ZKc;
-                const int clen = (nchunk + 1) * ZKc;
+                const int clen = round_up((nchunk + 1) * ZKc, 16);
                 pptr[N] = (long long)pvals.size();
                 pvals.resize(pvals.size() + clen, 0.0);
                 double* B = pvals.data() + pptr[N];
@@ -272,59 +277,71 @@ void build_device(dfb_filter_s& H) {
             Z.coef_pad = H.upload(pvals);
             Z.coef_pad_ptr = H.upload(pptr);
             Z.box_lines = maxlines;
-            Z.unit_bytes = round_up(maxlines * 128 + maxcoef * 8, 1024);
+            Z.box_bytes = maxlines * ZKc * 8;
+            Z.unit_bytes = round_up(Z.box_bytes + maxcoef * 8, ZKc == 16 ? 1024 : 512);   // the swizzle pattern repeats every 1024 (512) bytes
             Z.smem_bytes = 4 * 2 * Z.unit_bytes + 4 * 2 * 8 + 4 * 2 * 64 + 1024;   // buffers, mbarriers, item descriptors, alignment slack
-            if (maxlines > 256) throw Error{DFB_ERR_ARG, "z half-width too large for the staged window (N_z <= 1700)"};
-            // items (row, strip), most expensive first; workers pull them from a counter
-            std::vector<ZItem> items;
-            std::vector<long long> cost;
-            for (int j = 0; j < Ny; ++j) {
-                ZItem it{};
-                it.j = j;
-                long long c = 0;
-                for (int f = 0; f < 3; ++f) {
+            if (maxlines > 256) throw Error{DFB_ERR_ARG, "z half-width too large for the staged window"};
+            // Units (row, strip, field) pulled from a counter by the persistent warps.  v' needs u's blended field
+            // (df.cpp:437): every u unit comes first (most expensive first), then w, then v; a v unit checks the
+            // completion flag of its u unit (set long before in practice; u units never wait, so no deadlock).
+            std::vector<ZUnit> units;
+            const int nstrips = (W + strip - 1) / strip;
+            const int forder[3] = {0, 2, 1};
+            for (int fi = 0; fi < 3; ++fi) {
+                const int f = forder[fi];
+                std::vector<ZUnit> group;
+                for (int j = 0; j < Ny; ++j) {
                     const int N = P.f[f].N_z_row[j];
-                    const int d = ((-N) % 16 + 16) % 16;
-                    it.nchunk[f] = 1 + (2 * N + d + ZKc - 1) / ZKc;
-                    it.cbytes[f] = (it.nchunk[f] + 1) * ZKc * (int)sizeof(double);
-                    it.coff16[f] = (int)(pptr[N] / 16);
-                    c += 2 * N + 48;
-                }
-                for (int c0 = 0; c0 < W; c0 += strip) {
-                    it.c0 = c0;
-                    for (int f = 0; f < 3; ++f) {
-                        const FieldDev& F = H.D[0].f[f];
-                        const int s0 = F.zoff + c0 + F.Nz_max - P.f[f].N_z_row[j];   // storage column of output c0's first tap
-                        it.line0[f] = s0 >> 4;                                       // (s0 & 15) == d by construction
+                    const int d = ((-N) % ZKc + ZKc) % ZKc;
+                    ZUnit u{};
+                    u.j = j; u.f = f;
+                    u.nchunk = 1 + (2 * N + d + ZKc - 1) / ZKc;
+                    u.cbytes = round_up((u.nchunk + 1) * ZKc, 16) * (int)sizeof(double);
+                    u.coff16 = (int)(pptr[N] / 16);
+                    const FieldDev& F = H.D[0].f[f];
+                    for (int si = 0; si < nstrips; ++si) {
+                        u.c0 = si * strip;
+                        u.line0 = (F.zoff + u.c0 + F.Nz_max - N) / ZKc;      // that column is d past a line boundary by construction
+                        u.flag = j * nstrips + si;
+                        group.push_back(u);
                     }
-                    items.push_back(it); cost.push_back(c);
                 }
+                std::stable_sort(group.begin(), group.end(), [](const ZUnit& a, const ZUnit& b2) { return a.nchunk > b2.nchunk; });
+                units.insert(units.end(), group.begin(), group.end());
             }
-            std::vector<int> order(items.size());
-            for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
-            std::stable_sort(order.begin(), order.end(), [&](int a, int b2) { return cost[a] > cost[b2]; });
-            std::vector<ZItem> sorted(items.size());
-            for (size_t i = 0; i < order.size(); ++i) sorted[i] = items[order[i]];
-            Z.items = H.upload(sorted);
-            Z.n_items = (int)sorted.size();
+            Z.units = H.upload(units);
+            Z.n_units = (int)units.size();
+            Z.flags = H.dalloc<int>((size_t)Ny * nstrips);
             Z.counter = H.dalloc<int>(1);
             Z.debug = std::getenv("DFB_DEBUG_Z") ? std::atoi(std::getenv("DFB_DEBUG_Z")) : 0;
+            Z.prof = H.dalloc<unsigned long long>(8);
             cudaDeviceProp prop;
             CUDA_TRY(cudaGetDeviceProperties(&prop, H.device));
-            const int zb = std::getenv("DFB_Z_BLOCKS_PER_SM") ? std::atoi(std::getenv("DFB_Z_BLOCKS_PER_SM")) : 2;
-            Z.nblocks = std::max(1, std::min(zb * prop.multiProcessorCount, (Z.n_items + 3) / 4));
-            CUDA_TRY(zsweep_prepare((size_t)Z.smem_bytes));
+            int zb = 1;
+            CUDA_TRY(zsweep_prepare(Z.zk, (size_t)Z.smem_bytes, &zb));
+            if (std::getenv("DFB_Z_BLOCKS_PER_SM")) zb = std::min(zb, std::atoi(std::getenv("DFB_Z_BLOCKS_PER_SM")));
+            Z.nblocks = std::max(1, std::min(std::max(zb, 1) * prop.multiProcessorCount, (Z.n_units + 3) / 4));
+            Z.n_sm = prop.multiProcessorCount;
+            {
+                // one unit's tap loop when the fp64 pipe is shared by all co-resident warps of an SMSP; slots start 1/zb of that apart
+                double taps = 0;
+                for (const ZUnit& u : units) taps += (double)u.nchunk * ZKc * ZKc;
+                const double unit_cycles = 2.0 * taps / std::max<size_t>(units.size(), 1) * std::max(zb, 1);
+                const char* se = std::getenv("DFB_Z_STAGGER");
+                Z.stagger_cycles = se ? std::atoi(se) : 0;   // measured: no effect (co-resident warps spread out by themselves)
+                (void)unit_cycles;
+            }
             H.yp[0].zcounter = Z.counter;
             H.yp[1].zcounter = Z.counter;
             for (int b = 0; b < 2; ++b)
                 for (int f = 0; f < 3; ++f) {
                     const FieldDev& F = H.D[b].f[f];
-                    cuuint64_t dims[3] = {16, (cuuint64_t)(F.pitch_z / 16), (cuuint64_t)Ny};
-                    cuuint64_t strides[2] = {128, (cuuint64_t)F.pitch_z * sizeof(double)};
-                    cuuint32_t box[3] = {16u, (cuuint32_t)Z.box_lines, 1u};
+                    cuuint64_t dims[3] = {(cuuint64_t)Z.zk, (cuuint64_t)(F.pitch_z / Z.zk), (cuuint64_t)Ny};
+                    cuuint64_t strides[2] = {(cuuint64_t)Z.zk * 8, (cuuint64_t)F.pitch_z * sizeof(double)};
+                    cuuint32_t box[3] = {(cuuint32_t)Z.zk, (cuuint32_t)Z.box_lines, 1u};
                     cuuint32_t estr[3] = {1u, 1u, 1u};
                     CUresult r = encode_tiled()(&H.zmaps[b].m[f], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, F.r_zs, dims, strides, box, estr,
-                                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                                CU_TENSOR_MAP_INTERLEAVE_NONE, Z.zk == 16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
                     if (r != CUDA_SUCCESS) throw Error{DFB_ERR_CUDA, "cuTensorMapEncodeTiled (z) failed (" + std::to_string((int)r) + ")"};
                 }
@@ -425,7 +442,7 @@ void run_step(dfb_filter_s& H, double dt, bool first) {
         S.sa[f] = std::sqrt(alpha);                                // df.cpp:415
         S.sb[f] = std::sqrt(1.0 - alpha);
     }
-    if (H.tuned) { H.zp[b].S = S; CUDA_TRY(launch_zsweep_tuned(H.zmaps[b], H.zp[b], H.stream)); }
+    if (H.tuned) { H.zp[b].S = S; H.zp[b].stamp = (int)(H.step + 1); CUDA_TRY(launch_zsweep_tuned(H.zmaps[b], H.zp[b], H.stream)); }
     else CUDA_TRY(launch_zsweep_simple(H.D[b], S, H.stream));
     CUDA_TRY(cudaEventRecord(H.ev_free[b], H.stream));
     if (H.timing) CUDA_TRY(cudaEventRecord(H.ev[3], H.stream));
@@ -792,6 +809,16 @@ int dfb_measure_fp64_peak(int device, double* tflops, double* sm_mhz_est) {
         *tflops = 2.0 * fma / (best * 1e-3) / 1e12;
         if (sm_mhz_est) *sm_mhz_est = fma / (best * 1e-3) / (prop.multiProcessorCount * 64.0) / 1e6;   // if 64 DFMA/clk/SM
         cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(d);
+    });
+}
+
+int dfb_debug_zprof(dfb_handle h, unsigned long long* out8) {
+    if (!h || !out8) return fail(DFB_ERR_ARG, "bad argument");
+    return guarded([&] {
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        if (!h->zp[0].prof) throw Error{DFB_ERR_STATE, "no profile buffer"};
+        CUDA_TRY(cudaMemcpy(out8, h->zp[0].prof, 64, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemset(h->zp[0].prof, 0, 64));
     });
 }
 

@@ -101,30 +101,37 @@ struct YParams {
     PlaneDev D;
 };
 
-struct ZItem {                     // one row x one strip of 512 columns: 16 ints, everything a unit needs precomputed
-    int j, c0;
-    int nchunk[3];                 // tap-loop chunks per field
-    int line0[3];                  // first 128-byte line of the staged window per field
-    int cbytes[3];                 // bytes of the padded coefficient vector per field
-    int coff16[3];                 // offset of the padded coefficient vector in coef_pad, in units of 16 doubles
-    int pad_[2];
+struct ZUnit {                     // one row x one strip of 32*zk columns x one field: 8 ints
+    int j, c0, f;
+    int nchunk;                    // tap-loop chunks
+    int line0;                     // first line (zk doubles) of the staged window
+    int cbytes;                    // bytes of the padded coefficient vector
+    int coff16;                    // offset of the padded coefficient vector in coef_pad, in units of 16 doubles
+    int flag;                      // index of the (row, strip) completion flag: set by the u unit, awaited by the v unit
 };
-static_assert(sizeof(ZItem) == 64, "ZItem is loaded as 16 ints, one per lane");
+static_assert(sizeof(ZUnit) == 32, "ZUnit is loaded as 8 ints, one per lane");
 struct ZMaps { CUtensorMap m[3]; };   // r_zs[f] as {16 doubles, pitch/16 lines, Ny rows}, 128-byte swizzle
 
 struct ZParams {
     PlaneDev D;
     StepConsts S;
-    const ZItem* items;          // most expensive first
-    int n_items;
+    const ZUnit* units;          // all u units (most expensive first), then all w units, then all v units
+    int n_units;
+    int* flags;                  // [rows x strips]: step stamp written when the u unit of that strip has stored its blended field
+    int stamp;                   // this launch's stamp (step + 1)
     int* counter;                // work counter, zeroed by the y-sweep that precedes this launch
     const double* coef_pad;      // padded coefficient vectors B_N[m] = b_N[m - 16 - d(N)], zero elsewhere
     const long long* coef_pad_ptr;   // [Nmax+1] offsets (doubles, 16-byte aligned) into coef_pad
-    int box_lines;               // 128-byte lines per staged window (box height of the tensor maps)
+    int zk;                      // outputs per lane: 16 (128-byte lines) or 8 (64-byte lines); an item is 32*zk columns
+    int box_lines;               // lines per staged window (box height of the tensor maps)
+    int box_bytes;               // box_lines * zk * 8
     int unit_bytes;              // bytes per staging buffer: box_lines*128 + padded coefficient vector, 1024-aligned
     int nblocks;
     int smem_bytes;
+    int n_sm;                    // CTAs are dealt round-robin to the SMs: CTA b sits in residency slot b / n_sm of its SM
+    int stagger_cycles;          // start-up delay per residency slot (see the kernel): keeps co-resident warps out of phase
     int debug;                   // development probes only (0 in production)
+    unsigned long long* prof;    // [8] cycle counters filled when debug & 16
 };
 
 }  // namespace dfb

@@ -312,8 +312,6 @@ __device__ __forceinline__ double epi_blend(double fo, double sa, double z, doub
 __device__ __forceinline__ double epi_scale(double rc, double z) { return __dmul_rn(rc, z); }
 __device__ __forceinline__ double epi_cross(double rc1, double uf, double o) { return __fma_rn(rc1, uf, o); }
 
-constexpr int ZK = 16;                 // outputs per lane
-constexpr int Z_STRIP = 32 * ZK;       // columns per item
 
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
     asm volatile(
@@ -321,239 +319,273 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
         ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
 }
 
-__device__ __forceinline__ void z_issue_unit(const ZParams& P, const ZMaps& maps, const int* desc, int f, void* buf, uint64_t* bar) {
+__device__ __forceinline__ void z_issue_unit(const ZParams& P, const ZMaps& maps, const int* desc, void* buf, uint64_t* bar) {
     // called by one lane: two TMA operations land the unit's window and coefficient vector on `bar`.
     // The buffer was last touched through the generic proxy (tap-loop reads, transpose scratch):
     // order those accesses before the async-proxy writes of the TMA engine.
-    // desc = ZItem as 16 ints in shared memory: [0] j, [1] c0, [2..4] nchunk, [5..7] line0, [8..10] cbytes, [11..13] coff16
+    // desc = ZUnit as 8 ints in shared memory: [0] j, [1] c0, [2] f, [3] nchunk, [4] line0, [5] cbytes, [6] coff16, [7] flag
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    const uint32_t cbytes = (uint32_t)desc[8 + f];
-    mbar_expect_tx(bar, (uint32_t)(P.box_lines * 128) + cbytes);
-    tma_load_3d(buf, &maps.m[f], 0, desc[5 + f], desc[0], bar);
-    tma_load_1d(reinterpret_cast<unsigned char*>(buf) + P.box_lines * 128, P.coef_pad + (size_t)desc[11 + f] * 16, cbytes, bar);
+    const uint32_t cbytes = (uint32_t)desc[5];
+    mbar_expect_tx(bar, (uint32_t)P.box_bytes + cbytes);
+    tma_load_3d(buf, &maps.m[desc[2]], 0, desc[4], desc[0], bar);
+    tma_load_1d(reinterpret_cast<unsigned char*>(buf) + P.box_bytes, P.coef_pad + (size_t)desc[6] * 16, cbytes, bar);
 }
 
+template <int ZK>
 __global__ void __launch_bounds__(128) zsweep_epilogue_kernel(const __grid_constant__ ZMaps maps, const ZParams P) {
+    constexpr int Z_STRIP = 32 * ZK;         // columns per unit
+    constexpr int LB = ZK * 8;               // bytes per staged line (= one lane's ZK samples): 128 -> SWIZZLE_128B, 64 -> SWIZZLE_64B
+    constexpr int PPL = ZK / 2;              // 16-byte pieces per line
+    // hardware swizzle of the TMA box: the 16-byte piece index is XORed with address bits [7:9] (128B mode) or [7:8] (64B mode)
+    auto swz = [](int line) { return ZK == 16 ? (line & 7) : ((line >> 1) & 3); };
     extern __shared__ __align__(1024) unsigned char zsm_unaligned[];
-    // the 128-byte swizzle is a function of the shared-memory address: put the buffers on a 1 KiB boundary
+    // the swizzle is a function of the shared-memory address: put the buffers on a 1 KiB boundary
     unsigned char* zsm_raw = zsm_unaligned + ((1024u - (smem_u32(zsm_unaligned) & 1023u)) & 1023u);
     const PlaneDev& D = P.D;
-    // Warp index through a shuffle: the compiler then knows every address derived from it is warp-uniform and
-    // keeps the (warp-broadcast) coefficients in uniform registers -- DFMA R, R.reuse, UR, R needs one fresh
-    // vector-register operand instead of two and runs at the fp64 pipe's full rate.  (For the same reason the
-    // field loop below must NOT be unrolled and the kernel carries no minBlocksPerSM hint: either makes ptxas
-    // fall back to vector registers for the coefficients, at ~70 % of the rate.)
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-    // per warp: 2 buffers of unit_bytes (window lines + coefficient vector); then 2 mbarriers and 2 item descriptors per warp
+    // per warp: 2 buffers of unit_bytes (window lines + coefficient vector); then 2 mbarriers and 2 unit descriptors per warp
     unsigned char* wbase = zsm_raw + (size_t)warp * 2 * P.unit_bytes;
     unsigned char* tail = zsm_raw + (size_t)4 * 2 * P.unit_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(tail) + warp * 2;
-    int* descs = reinterpret_cast<int*>(tail + 64) + warp * 32;              // [2][16]
+    int* descs = reinterpret_cast<int*>(tail + 64) + warp * 16;              // [2][8]
     if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
 
+    const long long tstart = (P.debug & 16) ? clock64() : 0;
+    // claim the first two units; stage the first
     int claim = 0;
     if (lane == 0) claim = atomicAdd(P.counter, 1);
-    int item = __shfl_sync(0xffffffffu, claim, 0);
-    if (item >= P.n_items) return;
-    if (lane < 16) descs[lane] = reinterpret_cast<const int*>(P.items + item)[lane];
+    int cur = __shfl_sync(0xffffffffu, claim, 0);
+    if (cur >= P.n_units) return;
+    if (lane < 8) descs[lane] = reinterpret_cast<const int*>(P.units + cur)[lane];
+    if (lane == 0) claim = atomicAdd(P.counter, 1);
+    int nxt = __shfl_sync(0xffffffffu, claim, 0);
+    if (nxt < P.n_units && lane < 8) descs[8 + lane] = reinterpret_cast<const int*>(P.units + nxt)[lane];
     __syncwarp();
-    if (lane == 0) z_issue_unit(P, maps, descs, 0, wbase, &bars[0]);
+    if (lane == 0) z_issue_unit(P, maps, descs, wbase, &bars[0]);
 
-    double uf[ZK];                       // u's blended filtered value, needed by v' (df.cpp:437)
-    int n = 0;                           // running unit index: buffer n & 1, barrier phase (n >> 1) & 1
-    for (int k = 0;; ++k) {              // k-th item of this warp; its descriptor lives in descs[(k & 1) * 16 ..]
-        const int* dcur = descs + (k & 1) * 16;
-        int* dnext = descs + ((k + 1) & 1) * 16;
-        const int j = dcur[0], c0 = dcur[1];
+    // Pipeline per unit n (buffer n & 1, barrier phase (n >> 1) & 1):
+    //   top:    stage unit n+1 (its descriptor is already in shared memory), claim unit n+2 (atomic, result not awaited)
+    //   middle: tap loop of unit n
+    //   bottom: epilogue of unit n; fetch the descriptor of unit n+2 into the slot unit n just vacated
+    for (int n = 0;; ++n) {
+        const int* dcur = descs + (n & 1) * 8;
+        int* dnext = descs + ((n + 1) & 1) * 8;
+        const bool have_next = nxt < P.n_units;
+        if (have_next && lane == 0) {
+            unsigned char* nb = wbase + (size_t)((n + 1) & 1) * P.unit_bytes;
+            z_issue_unit(P, maps, dnext, nb, &bars[(n + 1) & 1]);
+        }
+        if (have_next && lane == 0) claim = atomicAdd(P.counter, 1);        // unit n+2
+
+        const int j = dcur[0], c0 = dcur[1], f = dcur[2];
+        const int nchunk = __shfl_sync(0xffffffffu, dcur[3], 0);
+        const int flag_idx = dcur[7];
         const int k0 = c0 + lane * ZK;
         const bool active = k0 < D.W;
         const size_t base = (size_t)j * D.W + k0;
         const size_t sbase = (size_t)j * D.W + c0;                            // first cell of the warp's strip
-        const bool full = (k0 + ZK <= D.W) && ((base & 1) == 0);
         // whole strip inside the plane and 16-byte aligned: go through the shared-memory transpose (coalesced global access)
         const bool coalesced = (c0 + Z_STRIP <= D.W) && ((sbase & 1) == 0) && !(P.debug & 4);
-        const double* rcp = D.rowc + (size_t)j * ROWC;
-        const double rc1 = __ldg(rcp + 1), rc4 = __ldg(rcp + 4), rc5 = __ldg(rcp + 5), rc6 = __ldg(rcp + 6);
-        int next_item = 0, dreg = 0;
-        bool have_next = false;
+        const FieldDev& F = D.f[f];
+        const bool blend = !P.S.first_step;
+        const long long tunit = (P.debug & 16) ? clock64() : 0;
 
-#pragma unroll 1
-        for (int f = 0; f < 3; ++f, ++n) {
-            // ---- work-list look-ahead, spread over the item's three units so no latency is exposed ----
-            if (f == 0) {
-                if (lane == 0) claim = atomicAdd(P.counter, 1);              // claim the next item
-            } else if (f == 1) {
-                next_item = __shfl_sync(0xffffffffu, claim, 0);
-                have_next = next_item < P.n_items;
-                if (have_next && lane < 16) dreg = __ldg(reinterpret_cast<const int*>(P.items + next_item) + lane);
-            } else {
-                if (have_next && lane < 16) dnext[lane] = dreg;
-                __syncwarp();
-            }
-            // ---- stage the next unit while this one computes ----
-            const bool more = (f < 2) || have_next;
-            if (more && lane == 0) {
-                unsigned char* nb = wbase + (size_t)((n + 1) & 1) * P.unit_bytes;
-                if (f < 2) z_issue_unit(P, maps, dcur, f + 1, nb, &bars[(n + 1) & 1]);
-                else z_issue_unit(P, maps, dnext, 0, nb, &bars[(n + 1) & 1]);
-            }
-            const FieldDev& F = D.f[f];
-            const int nchunk = __shfl_sync(0xffffffffu, dcur[2 + f], 0);     // provably uniform trip count (see `warp` above)
-            const double rc_own = __ldg(rcp + (f == 0 ? 0 : (f == 1 ? 2 : 3)));
-            const bool blend = !P.S.first_step;
-
-            // filt_old of this field: requested before the tap loop, consumed after it
-            double2 fo[ZK / 2];
-            if (blend && !(P.debug & 1)) {
-                if (coalesced) {
+        // filt_old of this strip, coalesced (piece p = lane + 32 m): requested now, consumed after the tap loop
+        double2 fo_pc[ZK / 2];
+        if (blend && coalesced) {
 #pragma unroll
-                    for (int m = 0; m < ZK / 2; ++m)       // piece p = lane + 32 m of the strip: 512 contiguous bytes per instruction
-                        fo[m] = __ldcs(reinterpret_cast<const double2*>(F.filt_old + sbase) + lane + 32 * m);
-                } else if (full) {
-#pragma unroll
-                    for (int i = 0; i < ZK / 2; ++i) fo[i] = __ldcs(reinterpret_cast<const double2*>(F.filt_old + base) + i);
-                }
-            }
-
-            mbar_wait(&bars[n & 1], (n >> 1) & 1);
-            unsigned char* cbuf = wbase + (size_t)(n & 1) * P.unit_bytes;
-            // (address through a shuffle: provably warp-uniform -> coefficients in uniform registers)
-            const double* B = reinterpret_cast<const double*>(__cvta_shared_to_generic(
-                (size_t)__shfl_sync(0xffffffffu, smem_u32(cbuf + P.box_lines * 128), 0)));
-            double acc[ZK];
-            double w[2 * ZK - 1];
-#pragma unroll
-            for (int i = 0; i < ZK; ++i) acc[i] = 0.0;
-#pragma unroll
-            for (int i = 0; i < ZK - 1; ++i) w[i] = 0.0;
-            for (int ch = 0; ch < nchunk; ++ch) {
-                const int line = lane + ch;
-                const unsigned char* lp = cbuf + line * 128;
-                const int sw = (line & 7) << 4;          // 128-byte swizzle: 16-byte piece i lives at i ^ (line & 7)
-                double x[ZK];
-#pragma unroll
-                for (int i = 0; i < ZK / 2; ++i) {
-                    const double2 t = *reinterpret_cast<const double2*>(lp + ((i << 4) ^ sw));
-                    x[2 * i] = t.x; x[2 * i + 1] = t.y;
-                }
-#pragma unroll
-                for (int i = 0; i < ZK / 2; ++i) {
-                    const double2 t = *reinterpret_cast<const double2*>(B + ZK * ch + ZK + 2 * i);
-                    w[ZK - 1 + 2 * i] = t.x; w[ZK + 2 * i] = t.y;
-                }
-                // out[kk] += x[q] * b[(16 ch + q) - kk - d] = x[q] * w[q - kk + 15]      (df.cpp:397-399)
-#pragma unroll
-                for (int q = 0; q < ZK; ++q)
-#pragma unroll
-                    for (int kk = 0; kk < ZK; ++kk) acc[kk] = fma(x[q], w[q - kk + ZK - 1], acc[kk]);
-#pragma unroll
-                for (int i = 0; i < ZK - 1; ++i) w[i] = w[i + ZK];
-            }
-            __syncwarp();                // every lane is done with this buffer's window: it becomes the transpose scratch
-
-            if (!((P.debug & 2) && acc[0] != 123.456)) {
-                // ---- epilogue for this field ----
-                const double sa = P.S.sa[f], sb = P.S.sb[f];
-                if (coalesced) {
-                    // Lane l owns line l (its 16 cells) of a 32 x 128-byte scratch tile; global memory wants piece
-                    // p = lane + 32 m.  Both views are conflict-free under the same XOR swizzle.
-                    const int own = lane * 128, osw = (lane & 7) << 4;
-                    auto put_pieces = [&](const double2* v) {      // piece-major registers -> tile
-#pragma unroll
-                        for (int m = 0; m < ZK / 2; ++m) {
-                            const int r = (lane >> 3) + 4 * m;
-                            *reinterpret_cast<double2*>(cbuf + r * 128 + ((((lane & 7) ^ (r & 7))) << 4)) = v[m];
-                        }
-                    };
-                    auto get_pieces = [&](double2* v) {            // tile -> piece-major registers
-#pragma unroll
-                        for (int m = 0; m < ZK / 2; ++m) {
-                            const int r = (lane >> 3) + 4 * m;
-                            v[m] = *reinterpret_cast<const double2*>(cbuf + r * 128 + ((((lane & 7) ^ (r & 7))) << 4));
-                        }
-                    };
-                    auto put_own = [&](const double* v) {          // this lane's 16 cells -> its line
-#pragma unroll
-                        for (int i = 0; i < ZK / 2; ++i)
-                            *reinterpret_cast<double2*>(cbuf + own + ((i << 4) ^ osw)) = make_double2(v[2 * i], v[2 * i + 1]);
-                    };
-                    auto get_own = [&](double* v) {
-#pragma unroll
-                        for (int i = 0; i < ZK / 2; ++i) {
-                            const double2 t = *reinterpret_cast<const double2*>(cbuf + own + ((i << 4) ^ osw));
-                            v[2 * i] = t.x; v[2 * i + 1] = t.y;
-                        }
-                    };
-                    auto store_strip = [&](double* gstrip, const double* v, bool streaming) {
-                        double2 pc[ZK / 2];
-                        put_own(v);
-                        __syncwarp();
-                        get_pieces(pc);
-                        __syncwarp();
-#pragma unroll
-                        for (int m = 0; m < ZK / 2; ++m) {
-                            double2* dst = reinterpret_cast<double2*>(gstrip) + lane + 32 * m;
-                            if (streaming) __stcs(dst, pc[m]); else *dst = pc[m];
-                        }
-                    };
-                    double z[ZK];
-                    if (blend) {
-                        double own_fo[ZK];
-                        put_pieces(fo);
-                        __syncwarp();
-                        get_own(own_fo);
-                        __syncwarp();
-#pragma unroll
-                        for (int i = 0; i < ZK; ++i) z[i] = epi_blend(own_fo[i], sa, acc[i], sb);      // correlate_fields, df.cpp:415
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < ZK; ++i) z[i] = acc[i];
-                    }
-                    store_strip(F.filt_old + sbase, z, false);                                  // filt_old <- filt, df.cpp:440-442
-                    double o[ZK];
-#pragma unroll
-                    for (int i = 0; i < ZK; ++i) {
-                        o[i] = epi_scale(rc_own, z[i]);                                         // df.cpp:436,438; v.filt term of 437
-                        if (f == 0) uf[i] = z[i];
-                        if (f == 1) o[i] = epi_cross(rc1, uf[i], o[i]);                         // df.cpp:437
-                    }
-                    store_strip(F.fluc + sbase, o, true);
-                    if (f == 0 && blend) {                                                      // get_rho_T_fluc, df.cpp:474-481
-                        double t[ZK];
-#pragma unroll
-                        for (int i = 0; i < ZK; ++i) { z[i] = __dmul_rn(rc4, o[i]); t[i] = __dmul_rn(z[i], rc5); }
-                        store_strip(D.T_fluc + sbase, t, true);
-#pragma unroll
-                        for (int i = 0; i < ZK; ++i) t[i] = __dmul_rn(-z[i], rc6);
-                        store_strip(D.rho_fluc + sbase, t, true);
-                    }
-                } else if (active) {
-                    double* __restrict__ fold = F.filt_old + base;
-                    double* __restrict__ fluc = F.fluc + base;
-                    double* __restrict__ Tp = D.T_fluc + base;
-                    double* __restrict__ Rp = D.rho_fluc + base;
-#pragma unroll
-                    for (int i = 0; i < ZK; ++i) {
-                        if (k0 + i < D.W) {
-                            double za = acc[i];
-                            if (blend) za = epi_blend(full ? (i & 1 ? fo[i / 2].y : fo[i / 2].x) : fold[i], sa, za, sb);
-                            fold[i] = za;
-                            double oa = epi_scale(rc_own, za);
-                            if (f == 0) uf[i] = za;
-                            if (f == 1) oa = epi_cross(rc1, uf[i], oa);
-                            fluc[i] = oa;
-                            if (f == 0 && blend) {
-                                const double ta = __dmul_rn(rc4, oa);
-                                Tp[i] = __dmul_rn(ta, rc5);
-                                Rp[i] = __dmul_rn(-ta, rc6);
-                            }
-                        }
-                    }
-                }
-                __syncwarp();            // scratch reads are done before the buffer is refilled by the next-but-one unit
-            }
+            for (int m = 0; m < ZK / 2; ++m) fo_pc[m] = __ldcs(reinterpret_cast<const double2*>(F.filt_old + sbase) + lane + 32 * m);
         }
-        if (!have_next) break;
+        const long long t0 = (P.debug & 16) ? clock64() : 0;
+        mbar_wait(&bars[n & 1], (n >> 1) & 1);
+        const long long t1 = (P.debug & 16) ? clock64() : 0;
+        unsigned char* cbuf = wbase + (size_t)(n & 1) * P.unit_bytes;
+        const double* B = reinterpret_cast<const double*>(cbuf + P.box_bytes);
+        double acc[ZK];
+        double w[2 * ZK - 1];
+#pragma unroll
+        for (int i = 0; i < ZK; ++i) acc[i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < ZK - 1; ++i) w[i] = 0.0;
+        for (int ch = 0; ch < nchunk; ++ch) {
+            const int line = lane + ch;
+            const unsigned char* lp = cbuf + line * LB;
+            const int sw = swz(line) << 4;               // 16-byte piece i of a line lives at i ^ swz(line)
+            double x[ZK];
+#pragma unroll
+            for (int i = 0; i < ZK / 2; ++i) {
+                const double2 t = *reinterpret_cast<const double2*>(lp + ((i << 4) ^ sw));
+                x[2 * i] = t.x; x[2 * i + 1] = t.y;
+            }
+#pragma unroll
+            for (int i = 0; i < ZK / 2; ++i) {
+                const double2 t = *reinterpret_cast<const double2*>(B + ZK * ch + ZK + 2 * i);
+                w[ZK - 1 + 2 * i] = t.x; w[ZK + 2 * i] = t.y;
+            }
+            // out[kk] += x[q] * b[(ZK ch + q) - kk - d] = x[q] * w[q - kk + ZK - 1]      (df.cpp:397-399)
+#pragma unroll
+            for (int q = 0; q < ZK; ++q)
+#pragma unroll
+                for (int kk = 0; kk < ZK; ++kk) acc[kk] = fma(x[q], w[q - kk + ZK - 1], acc[kk]);
+#pragma unroll
+            for (int i = 0; i < ZK - 1; ++i) w[i] = w[i + ZK];
+        }
+        __syncwarp();                    // every lane is done with this buffer's window: it becomes the transpose scratch
+        const long long t2 = (P.debug & 16) ? clock64() : 0;
+
+        // ---- epilogue of this (strip, field) ----
+        {
+            const double* rcp = D.rowc + (size_t)j * ROWC;
+            const double rc_own = __ldg(rcp + (f == 0 ? 0 : (f == 1 ? 2 : 3)));
+            const double sa = P.S.sa[f], sb = P.S.sb[f];
+            if (f == 1) {
+                // v' = b u_filt + c v_filt (df.cpp:437): u's blended field of this strip comes from the u unit
+                // (queued far ahead of every v unit); wait for its stamp, then read it like any other global data
+                if (lane == 0) {
+                    const volatile int* fl = P.flags + flag_idx;
+                    while (*fl != P.stamp) __nanosleep(100);
+                }
+                __syncwarp();
+                __threadfence();
+            }
+            if (coalesced) {
+                // Lane l owns line l (its ZK cells) of a 32-line scratch tile; global memory wants piece
+                // p = lane + 32 m.  Both views are conflict-free under the same XOR swizzle.
+                const int own = lane * LB, osw = swz(lane) << 4;
+                auto put_pieces = [&](const double2* v) {      // piece-major registers -> tile
+#pragma unroll
+                    for (int m = 0; m < ZK / 2; ++m) {
+                        const int pc_ = lane + 32 * m, r = pc_ / PPL;
+                        *reinterpret_cast<double2*>(cbuf + r * LB + ((((pc_ % PPL) ^ swz(r))) << 4)) = v[m];
+                    }
+                };
+                auto get_pieces = [&](double2* v) {            // tile -> piece-major registers
+#pragma unroll
+                    for (int m = 0; m < ZK / 2; ++m) {
+                        const int pc_ = lane + 32 * m, r = pc_ / PPL;
+                        v[m] = *reinterpret_cast<const double2*>(cbuf + r * LB + ((((pc_ % PPL) ^ swz(r))) << 4));
+                    }
+                };
+                auto put_own = [&](const double* v) {          // this lane's ZK cells -> its line
+#pragma unroll
+                    for (int i = 0; i < ZK / 2; ++i)
+                        *reinterpret_cast<double2*>(cbuf + own + ((i << 4) ^ osw)) = make_double2(v[2 * i], v[2 * i + 1]);
+                };
+                auto get_own = [&](double* v) {
+#pragma unroll
+                    for (int i = 0; i < ZK / 2; ++i) {
+                        const double2 t = *reinterpret_cast<const double2*>(cbuf + own + ((i << 4) ^ osw));
+                        v[2 * i] = t.x; v[2 * i + 1] = t.y;
+                    }
+                };
+                auto load_strip = [&](const double* gstrip, double* v) {     // coalesced global read -> this lane's cells
+                    double2 pc[ZK / 2];
+#pragma unroll
+                    for (int m = 0; m < ZK / 2; ++m) pc[m] = __ldcg(reinterpret_cast<const double2*>(gstrip) + lane + 32 * m);
+                    put_pieces(pc);
+                    __syncwarp();
+                    get_own(v);
+                    __syncwarp();
+                };
+                auto store_strip = [&](double* gstrip, const double* v, bool streaming) {
+                    double2 pc[ZK / 2];
+                    put_own(v);
+                    __syncwarp();
+                    get_pieces(pc);
+                    __syncwarp();
+#pragma unroll
+                    for (int m = 0; m < ZK / 2; ++m) {
+                        double2* dst = reinterpret_cast<double2*>(gstrip) + lane + 32 * m;
+                        if (streaming) __stcs(dst, pc[m]); else *dst = pc[m];
+                    }
+                };
+                double z[ZK];
+                if (blend) {
+                    double fo[ZK];
+                    put_pieces(fo_pc);
+                    __syncwarp();
+                    get_own(fo);
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < ZK; ++i) z[i] = epi_blend(fo[i], sa, acc[i], sb);      // correlate_fields, df.cpp:415
+                } else {
+#pragma unroll
+                    for (int i = 0; i < ZK; ++i) z[i] = acc[i];
+                }
+                store_strip(F.filt_old + sbase, z, false);                                      // filt_old <- filt, df.cpp:440-442
+                double o[ZK];
+#pragma unroll
+                for (int i = 0; i < ZK; ++i) o[i] = epi_scale(rc_own, z[i]);                    // df.cpp:436,438; v.filt term of 437
+                if (f == 1) {
+                    const double rc1 = __ldg(rcp + 1);
+                    double uf[ZK];
+                    load_strip(D.f[0].filt_old + sbase, uf);
+#pragma unroll
+                    for (int i = 0; i < ZK; ++i) o[i] = epi_cross(rc1, uf[i], o[i]);            // df.cpp:437
+                }
+                store_strip(F.fluc + sbase, o, true);
+                if (f == 0 && blend) {                                                          // get_rho_T_fluc, df.cpp:474-481
+                    const double rc4 = __ldg(rcp + 4), rc5 = __ldg(rcp + 5), rc6 = __ldg(rcp + 6);
+                    double t[ZK];
+#pragma unroll
+                    for (int i = 0; i < ZK; ++i) { z[i] = __dmul_rn(rc4, o[i]); t[i] = __dmul_rn(z[i], rc5); }
+                    store_strip(D.T_fluc + sbase, t, true);
+#pragma unroll
+                    for (int i = 0; i < ZK; ++i) t[i] = __dmul_rn(-z[i], rc6);
+                    store_strip(D.rho_fluc + sbase, t, true);
+                }
+            } else if (active) {
+                double* __restrict__ fold = F.filt_old + base;
+                double* __restrict__ fluc = F.fluc + base;
+                const double* __restrict__ ufp = D.f[0].filt_old + base;
+                const double rc1 = __ldg(rcp + 1), rc4 = __ldg(rcp + 4), rc5 = __ldg(rcp + 5), rc6 = __ldg(rcp + 6);
+#pragma unroll
+                for (int i = 0; i < ZK; ++i) {
+                    if (k0 + i < D.W) {
+                        double za = acc[i];
+                        if (blend) za = epi_blend(fold[i], sa, za, sb);
+                        fold[i] = za;
+                        double oa = epi_scale(rc_own, za);
+                        if (f == 1) oa = epi_cross(rc1, __ldcg(ufp + i), oa);
+                        fluc[i] = oa;
+                        if (f == 0 && blend) {
+                            const double ta = __dmul_rn(rc4, oa);
+                            D.T_fluc[base + i] = __dmul_rn(ta, rc5);
+                            D.rho_fluc[base + i] = __dmul_rn(-ta, rc6);
+                        }
+                    }
+                }
+            }
+            if (f == 0) {                 // publish: this strip's blended u field is in global memory
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) *reinterpret_cast<volatile int*>(P.flags + flag_idx) = P.stamp;
+            }
+            __syncwarp();                // scratch reads are done before the buffer is refilled by the next-but-one unit
+        }
+        if ((P.debug & 16) && lane == 0) {
+            const long long t3 = clock64();
+            atomicAdd(P.prof + 0, (unsigned long long)(t1 - t0));     // waiting for the staged unit
+            atomicAdd(P.prof + 1, (unsigned long long)(t2 - t1));     // tap loop
+            atomicAdd(P.prof + 2, (unsigned long long)(t3 - t2));     // epilogue
+            atomicAdd(P.prof + 3, (unsigned long long)(t3 - tunit));  // whole unit
+            atomicAdd(P.prof + 4, 1ull);
+        }
+        if (!have_next) {
+            if ((P.debug & 16) && lane == 0) {
+                const unsigned long long life = (unsigned long long)(clock64() - tstart);
+                atomicAdd(P.prof + 5, life);
+                atomicMax(P.prof + 6, life);
+                atomicAdd(P.prof + 7, 1ull);
+            }
+            break;
+        }
+        // descriptor of unit n+2 into the slot unit n just vacated (the atomic was issued at the top of this unit)
+        const int nn = __shfl_sync(0xffffffffu, claim, 0);
+        int* dfree = descs + (n & 1) * 8;
+        if (nn < P.n_units && lane < 8) dfree[lane] = __ldg(reinterpret_cast<const int*>(P.units + nn) + lane);
+        __syncwarp();
+        nxt = nn;
     }
 }
 
@@ -617,17 +649,20 @@ cudaError_t launch_ysweep_tma(const YMaps& maps, const YParams& P, int n_tiles, 
     return cudaGetLastError();
 }
 
-int zsweep_strip() { return Z_STRIP; }
-int zsweep_k() { return ZK; }
+static const void* zsweep_fn(int zk) { return zk == 16 ? (const void*)zsweep_epilogue_kernel<16> : (const void*)zsweep_epilogue_kernel<8>; }
 
-cudaError_t zsweep_prepare(size_t smem) {
-    cudaError_t e = cudaFuncSetAttribute(zsweep_epilogue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+cudaError_t zsweep_prepare(int zk, size_t smem, int* blocks_per_sm) {
+    cudaError_t e = cudaFuncSetAttribute(zsweep_fn(zk), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(zsweep_epilogue_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    e = cudaFuncSetAttribute(zsweep_fn(zk), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    if (zk == 16) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, zsweep_epilogue_kernel<16>, 128, smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, zsweep_epilogue_kernel<8>, 128, smem);
 }
 
 cudaError_t launch_zsweep_tuned(const ZMaps& maps, const ZParams& P, cudaStream_t st) {
-    zsweep_epilogue_kernel<<<(unsigned)P.nblocks, 128, P.smem_bytes, st>>>(maps, P);
+    if (P.zk == 16) zsweep_epilogue_kernel<16><<<(unsigned)P.nblocks, 128, P.smem_bytes, st>>>(maps, P);
+    else zsweep_epilogue_kernel<8><<<(unsigned)P.nblocks, 128, P.smem_bytes, st>>>(maps, P);
     return cudaGetLastError();
 }
 

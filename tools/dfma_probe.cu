@@ -205,6 +205,41 @@ __global__ void __launch_bounds__(128) kG(double* out, const double* in, int ite
     if (s == 1.2345) out[0] = s;
 }
 
+// H: kF with the coefficient address made (trivially) lane-dependent: ptxas can no longer prove it warp-uniform,
+//    so the coefficients stay in vector registers -- the operand mix of the production z-sweep
+__global__ void __launch_bounds__(128) kH(double* out, const double* in, int iters, int zero) {
+    __shared__ __align__(16) double sx[160 * 18 + 64];
+    __shared__ __align__(16) double sb[640];
+    for (int i = threadIdx.x; i < 160 * 18 + 64; i += 128) sx[i] = in[i % 64];
+    for (int i = threadIdx.x; i < 640; i += 128) sb[i] = in[i % 64];
+    __syncthreads();
+    const double* xs = sx + threadIdx.x * 18;
+    const double* bb = sb + threadIdx.x * zero;      // always + 0, but not provably uniform
+    double acc[16], w[31];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 15; ++i) w[i] = 0;
+    for (int it = 0; it < iters; ++it) {
+        for (int ch = 0; ch < 16; ++ch) {
+            double x[16];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { const double2 t = *reinterpret_cast<const double2*>(xs + ch * 18 + 2 * i); x[2 * i] = t.x; x[2 * i + 1] = t.y; }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { const double2 t = *reinterpret_cast<const double2*>(bb + 16 * ch + 16 + 2 * i); w[15 + 2 * i] = t.x; w[16 + 2 * i] = t.y; }
+#pragma unroll
+            for (int q = 0; q < 16; ++q)
+#pragma unroll
+                for (int kk = 0; kk < 16; ++kk) acc[kk] = fma(x[q], w[q - kk + 15], acc[kk]);
+#pragma unroll
+            for (int i = 0; i < 15; ++i) w[i] = w[i + 16];
+        }
+    }
+    double s = 0;
+    for (int i = 0; i < 16; ++i) s += acc[i];
+    if (s == 1.2345) out[0] = s;
+}
+
 template <class F>
 static double timeit(F f) {
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
@@ -227,9 +262,10 @@ int main() {
         double tE = timeit([&] { kE<<<blocks, 128>>>(out, in, iters / 2); });
         double tF = timeit([&] { kF<<<blocks, 128>>>(out, in, iters / 8); });
         double tG = timeit([&] { kG<<<blocks, 128>>>(out, in, iters); });
+        double tH = timeit([&] { kH<<<blocks, 128>>>(out, in, iters / 8, 0); });
         double fE = 2.0 * blocks * 128.0 * (iters / 2) * 512, fF = 2.0 * blocks * 128.0 * (iters / 8) * 16 * 256, fG = 2.0 * blocks * 128.0 * iters * 256;
         double fA = 2.0 * blocks * 128.0 * iters * 8 * 32, fB = 2.0 * blocks * 128.0 * iters * 8 * 32, fC = 2.0 * blocks * 128.0 * iters * 256, fD = 2.0 * blocks * 128.0 * (iters / 4) * 32 * 64;
-        printf("blocks/SM=%d (warps/SMSP=%d)  A %.2f  B %.2f  C %.2f  D %.2f  E %.2f  F %.2f  G %.2f TFLOP/s\n", bps, bps, fA / tA / 1e12, fB / tB / 1e12, fC / tC / 1e12, fD / tD / 1e12, fE / tE / 1e12, fF / tF / 1e12, fG / tG / 1e12);
+        printf("blocks/SM=%d (warps/SMSP=%d)  A %.2f  B %.2f  C %.2f  D %.2f  E %.2f  F %.2f  G %.2f  H %.2f TFLOP/s\n", bps, bps, fA / tA / 1e12, fB / tB / 1e12, fC / tC / 1e12, fD / tD / 1e12, fE / tE / 1e12, fF / tF / 1e12, fG / tG / 1e12, fF / tH / 1e12);
     }
     cudaError_t e = cudaDeviceSynchronize();
     printf("%s\n", cudaGetErrorString(e));
