@@ -61,6 +61,9 @@ struct dfb_filter_s {
     PlaneDev D[2]{};
     bool overlap = true;
     int64_t buf_step[2] = {-1, -1};   // which step's noise set b currently holds (or -1)
+    int64_t ybuf_step[2] = {-1, -1};  // which step's y-sweep result the r_zs interior of set b holds (or -1)
+    bool y_ahead = false;             // optionally run the next step's y-sweep on the side stream too (measured: contention
+                                      // with the z-sweep costs more than the filled tail gains; off by default)
     int noise_view = 0;               // set holding the most recently consumed / generated noise
     cudaEvent_t ev_noise[2] = {nullptr, nullptr};   // noise into set b complete (either stream)
     cudaEvent_t ev_free[2] = {nullptr, nullptr};    // last readers of set b complete (main stream)
@@ -229,6 +232,8 @@ void build_device(dfb_filter_s& H) {
         H.yp[0].tiles = H.upload(tiles);
         H.yp[0].cmat = H.upload(cmat);
         H.yp[0].D = H.D[0];
+        H.yp[0].prof = H.dalloc<unsigned long long>(8);
+        H.yp[0].debug = std::getenv("DFB_DEBUG_Y") ? std::atoi(std::getenv("DFB_DEBUG_Y")) : 0;
         H.yp[1] = H.yp[0];
         H.yp[1].D = H.D[1];
         H.n_items = (int)tiles.size();
@@ -312,7 +317,7 @@ void build_device(dfb_filter_s& H) {
             Z.units = H.upload(units);
             Z.n_units = (int)units.size();
             Z.flags = H.dalloc<int>((size_t)Ny * nstrips);
-            Z.counter = H.dalloc<int>(1);
+            Z.counter = H.dalloc<int>(2);        // one work counter per buffer set: y(s+1) resets its own while z(s) still pulls from the other
             Z.debug = std::getenv("DFB_DEBUG_Z") ? std::atoi(std::getenv("DFB_DEBUG_Z")) : 0;
             Z.prof = H.dalloc<unsigned long long>(8);
             cudaDeviceProp prop;
@@ -332,7 +337,7 @@ void build_device(dfb_filter_s& H) {
                 (void)unit_cycles;
             }
             H.yp[0].zcounter = Z.counter;
-            H.yp[1].zcounter = Z.counter;
+            H.yp[1].zcounter = Z.counter + 1;
             for (int b = 0; b < 2; ++b)
                 for (int f = 0; f < 3; ++f) {
                     const FieldDev& F = H.D[b].f[f];
@@ -348,6 +353,7 @@ void build_device(dfb_filter_s& H) {
         }
         H.zp[1] = Z;
         H.zp[1].D = H.D[1];
+        H.zp[1].counter = Z.counter + 1;
         
     }
 
@@ -413,6 +419,7 @@ void fill_noise_params(dfb_filter_s& H, int64_t step) {
 }
 
 void launch_noise_for(dfb_filter_s& H, int64_t step, int b, cudaStream_t st) {
+    H.ybuf_step[b] = -1;                 // new noise invalidates whatever y-sweep result the set held
     fill_noise_params(H, step);
     CUDA_TRY(launch_noise(H.np, H.D[b], st));
     CUDA_TRY(cudaEventRecord(H.ev_noise[b], st));
@@ -431,7 +438,9 @@ void run_step(dfb_filter_s& H, double dt, bool first) {
     }
     H.noise_view = b;
     if (H.timing) CUDA_TRY(cudaEventRecord(H.ev[1], H.stream));
-    if (H.tuned) CUDA_TRY(launch_ysweep_tma(H.maps[b], H.yp[b], H.n_items, H.stream));
+    if (H.noise_mode == DFB_NOISE_GENERATE && H.ybuf_step[b] == H.step) {
+        // this step's y-sweep already ran (or is running) on the side stream; ev_noise[b] above covers it
+    } else if (H.tuned) CUDA_TRY(launch_ysweep_tma(H.maps[b], H.yp[b], H.n_items, H.stream));
     else CUDA_TRY(launch_ysweep_simple(H.D[b], H.stream));
     if (H.timing) CUDA_TRY(cudaEventRecord(H.ev[2], H.stream));
     StepConsts S{};
@@ -454,6 +463,13 @@ void run_step(dfb_filter_s& H, double dt, bool first) {
         const int nb = (int)(H.step & 1);
         CUDA_TRY(cudaStreamWaitEvent(H.side, H.ev_free[nb], 0));     // readers of that set (step-2... ) are done
         launch_noise_for(H, H.step, nb, H.side);
+        // ... and so does its y-sweep (it reads only that noise and writes only that set's r_zs interior): it
+        // becomes resident as this step's z-sweep CTAs retire and keeps the fp64 pipe busy through the tail.
+        if (H.tuned && H.y_ahead) {
+            CUDA_TRY(launch_ysweep_tma(H.maps[nb], H.yp[nb], H.n_items, H.side));
+            CUDA_TRY(cudaEventRecord(H.ev_noise[nb], H.side));      // "set nb is ready" now means noise + y-sweep
+            H.ybuf_step[nb] = H.step;
+        }
     }
     if (H.timing) {
         CUDA_TRY(cudaEventSynchronize(H.ev[3]));
@@ -521,6 +537,7 @@ int dfb_create(const dfb_config* cfg, dfb_handle* out) {
         CUDA_TRY(cudaSetDevice(dev));
         if (cfg->noise_mode != DFB_NOISE_GENERATE && cfg->noise_mode != DFB_NOISE_INJECT) throw Error{DFB_ERR_ARG, "bad noise_mode"};
         H->noise_mode = cfg->noise_mode;
+        H->y_ahead = std::getenv("DFB_Y_AHEAD") != nullptr;
         H->kernel_variant = cfg->kernel_variant;
         H->seed = cfg->seed;
         H->plane_id = cfg->plane_id;
@@ -809,6 +826,16 @@ int dfb_measure_fp64_peak(int device, double* tflops, double* sm_mhz_est) {
         *tflops = 2.0 * fma / (best * 1e-3) / 1e12;
         if (sm_mhz_est) *sm_mhz_est = fma / (best * 1e-3) / (prop.multiProcessorCount * 64.0) / 1e6;   // if 64 DFMA/clk/SM
         cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(d);
+    });
+}
+
+int dfb_debug_yprof(dfb_handle h, unsigned long long* out8) {
+    if (!h || !out8) return fail(DFB_ERR_ARG, "bad argument");
+    return guarded([&] {
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        if (!h->yp[0].prof) throw Error{DFB_ERR_STATE, "no profile buffer"};
+        CUDA_TRY(cudaMemcpy(out8, h->yp[0].prof, 64, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemset(h->yp[0].prof, 0, 64));
     });
 }
 

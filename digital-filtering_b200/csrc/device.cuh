@@ -98,6 +98,8 @@ struct YParams {
     const YTile* tiles;
     const double* cmat;
     int* zcounter;             // work counter of the z-sweep that follows (reset here)
+    unsigned long long* prof;  // [8] cycle counters (development probe, filled when debug != 0)
+    int debug;
     PlaneDev D;
 };
 

@@ -21,9 +21,9 @@ namespace dfb {
 // H1: white noise
 // =================================================================================================
 __global__ void __launch_bounds__(128) noise_kernel(const NoiseParams P, const PlaneDev D) {
-    const NoiseArray& A = P.a[blockIdx.y];
-    const int seg = blockIdx.x / P.chunks;
-    const int slot = (blockIdx.x % P.chunks) * blockDim.x + threadIdx.x;
+    const NoiseArray& A = P.a[blockIdx.z];
+    const int seg = blockIdx.y;
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (seg >= A.n_seg) return;
     const int np = A.seg_np[seg];
     if (slot >= np) return;
@@ -237,10 +237,15 @@ __global__ void __launch_bounds__(160, 3) ysweep_tma_kernel(const __grid_constan
 #pragma unroll
     for (int jj = 0; jj < YJ; ++jj) { acc[jj][0] = acc[jj][1] = acc[jj][2] = acc[jj][3] = 0.0; }
 
+    long long tw = 0, tc = 0;
+    const long long tstart = P.debug ? clock64() : 0;
     int i = 0;
     for (int c = t.cbegin; c < t.cend; ++c, ++i) {
         const int s = i % NS;
+        const long long ta = P.debug ? clock64() : 0;
         mbar_wait(&sm.full[s], (i / NS) & 1);
+        const long long tb = P.debug ? clock64() : 0;
+        tw += tb - ta;
         if (c >= my_cs && c < my_ce) {
 #pragma unroll
             for (int r = 0; r < RC; ++r) {
@@ -262,7 +267,9 @@ __global__ void __launch_bounds__(160, 3) ysweep_tma_kernel(const __grid_constan
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.empty[s]);
+        if (P.debug) tc += clock64() - tb;
     }
+    const long long tloop = P.debug ? clock64() : 0;
     if (!have) return;
 
     // r_zs interior (df.cpp:377): extended column x -> logical column x + yshift
@@ -282,6 +289,15 @@ __global__ void __launch_bounds__(160, 3) ysweep_tma_kernel(const __grid_constan
                 if (x + 1 < F.We) dst[x + 1] = acc[jj][2 * h + 1];
             }
         }
+    }
+    if (P.debug && lane == 0) {
+        const long long tend = clock64();
+        atomicAdd(P.prof + 0, (unsigned long long)tw);                 // consumer waits on full barriers
+        atomicAdd(P.prof + 1, (unsigned long long)tc);                 // chunk compute (incl. skipped chunks)
+        atomicAdd(P.prof + 2, (unsigned long long)(tend - tloop));     // stores
+        atomicAdd(P.prof + 3, (unsigned long long)(tend - tstart));    // whole tile (after setup)
+        atomicAdd(P.prof + 4, 1ull);
+        atomicAdd(P.prof + 5, (unsigned long long)(t.cend - t.cbegin));
     }
 }
 
@@ -612,7 +628,7 @@ cudaError_t launch_noise(const NoiseParams& P, const PlaneDev& D, cudaStream_t s
     if (P.n_arrays == 0) return cudaSuccess;
     int max_seg = 0;
     for (int a = 0; a < P.n_arrays; ++a) max_seg = P.a[a].n_seg > max_seg ? P.a[a].n_seg : max_seg;
-    dim3 grid((unsigned)(max_seg * P.chunks), (unsigned)P.n_arrays);
+    dim3 grid((unsigned)P.chunks, (unsigned)max_seg, (unsigned)P.n_arrays);
     noise_kernel<<<grid, 128, 0, st>>>(P, D);
     return cudaGetLastError();
 }

@@ -1,0 +1,15 @@
+import ctypes, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
+import _dfb_import, digital_filtering_b200 as dfb
+from digital_filtering_b200 import workloads as W
+name = sys.argv[1] if len(sys.argv) > 1 else "1024x2048_saturated_N128"
+df = dfb.DIGITAL_FILTER(dfb.DFConfig.from_plane(W.NAMED[name](), seed=1), fetch=False)
+L = dfb.lib(); L.dfb_debug_yprof.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+out = (ctypes.c_uint64 * 8)()
+for _ in range(3): df.filter(1e-7)
+L.dfb_debug_yprof(df._h, out)
+df.set_timing(True)
+df.filter(1e-7); ms = df.last_ms()
+L.dfb_debug_yprof(df._h, out)
+v = list(out); n = max(v[4], 1)
+print(name, "y ms", ms["ysweep"], "warp-tiles", v[4], "per warp-tile cycles: wait %.0f  compute %.0f  store %.0f  whole %.0f  chunks %.1f" % (v[0]/n, v[1]/n, v[2]/n, v[3]/n, v[5]/n))
