@@ -34,6 +34,25 @@ METRIC = "inflow cell-updates/sec per filter() step"
 DT = 1e-7
 
 
+def ncu_traffic(kernel, workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full summary
+    (profiles/ncu_full_r01b_summary.csv, captured on the 1024x2048 profile workload); None for other workloads."""
+    if workload != DEFAULT_WORKLOAD:
+        return None
+    try:
+        import csv
+        rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "ncu_full_r01b_summary.csv"))))
+        col = [i for i, h in enumerate(rows[0]) if kernel.split("<")[0] in h][0]
+        tot = 0.0
+        for r in rows[1:]:
+            if r[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[r[1]]
+                tot += float(r[col]) * scale
+        return tot or None
+    except Exception:
+        return None
+
+
 def load_peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -283,7 +302,7 @@ def run_b200(args, plane):
     alg_bytes = 88 * cells                                    # 5 outputs + filt_old r/w x3
     step_ms = ms_total / K
     roofline = dict(bound="fp64", kernel=dom, achieved=kern[dom]["tflops"], peak=fp64_peak, unit="TFLOP/s", frac=kern[dom]["frac_fp64"],
-                    traffic=None, peak_source="DFMA microbenchmark measured live in this run (dfb_measure_fp64_peak); MEASURED_PEAKS.json has no fp64 entry",
+                    traffic=ncu_traffic(dom, plane["name"]), traffic_source="profiles/ncu_full_r01b_summary.csv (ncu --set full, one launch)", peak_source="DFMA microbenchmark measured live in this run (dfb_measure_fp64_peak); MEASURED_PEAKS.json has no fp64 entry",
                     step=dict(tflops=2 * (taps_y + taps_z) / (step_ms * 1e-3) / 1e12, frac_fp64=2 * (taps_y + taps_z) / (step_ms * 1e-3) / 1e12 / fp64_peak,
                               hbm_gbs=alg_bytes / (step_ms * 1e-3) / 1e9, frac_hbm=alg_bytes / (step_ms * 1e-3) / 1e9 / hbm_peak, hbm_peak=hbm_peak,
                               hbm_peak_source=hbm_src, binding="fp64" if 2 * (taps_y + taps_z) / fp64_peak / 1e12 > alg_bytes / hbm_peak / 1e9 else "hbm"),

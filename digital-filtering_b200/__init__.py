@@ -88,6 +88,9 @@ def lib():
         L.dfb_set_timing.argtypes = [C.c_void_p, C.c_int]
         L.dfb_last_ms.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float)]
         L.dfb_measure_fp64_peak.argtypes = [C.c_int, c_dp, c_dp]
+        L.dfb_stats_enable.argtypes = [C.c_void_p, C.c_int]
+        L.dfb_stats_get.argtypes = [C.c_void_p, C.c_int, C.c_int, c_dp, C.POINTER(C.c_int64)]
+        L.dfb_write_csv.argtypes = [C.c_void_p, C.c_char_p]
         _lib = L
     return _lib
 
@@ -361,6 +364,21 @@ class DIGITAL_FILTER:
     def set_state(self, filt_old, step):
         fo = np.ascontiguousarray(filt_old, dtype=np.float64) if filt_old is not None else None
         _check(lib().dfb_set_state(self._h, _dptr(fo), int(step)))
+
+    # ---- N2 running statistics / N4 CSV (both opt-in; filter() itself never writes or accumulates) ----
+    def stats_enable(self, on=True):
+        _check(lib().dfb_stats_enable(self._h, int(on)))
+
+    def stats(self, which, rms=False):
+        """which: 0 u'^2, 1 v'^2, 2 w'^2, 3 T'^2, 4 rho'^2, 5 u'v' (per-cell sums, or sqrt(sum/count) with rms=True).
+        Returns (array, accumulated steps)."""
+        out = np.zeros((self.Ny, self.Nz))
+        cnt = C.c_int64()
+        _check(lib().dfb_stats_get(self._h, which, int(rms), _dptr(out), C.byref(cnt)))
+        return out, cnt.value
+
+    def write_csv(self, path):
+        _check(lib().dfb_write_csv(self._h, str(path).encode()))
 
     # ---- timing ----
     def set_timing(self, on=True):

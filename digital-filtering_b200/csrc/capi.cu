@@ -3,6 +3,7 @@
 // There is no CPU fallback: without an sm_100 device dfb_create fails with DFB_ERR_CUDA.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -77,6 +78,10 @@ struct dfb_filter_s {
     // noise
     std::vector<NoiseHost> noise;
     NoiseParams np{};
+    // N2: running statistics (opt-in)
+    double* stats = nullptr;          // [6][Ny*W]: sum u'^2, v'^2, w'^2, T'^2, rho'^2, u'v'
+    int64_t stats_count = 0;
+    bool stats_on = false;
     // timing
     bool timing = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -453,6 +458,7 @@ void run_step(dfb_filter_s& H, double dt, bool first) {
     }
     if (H.tuned) { H.zp[b].S = S; H.zp[b].stamp = (int)(H.step + 1); CUDA_TRY(launch_zsweep_tuned(H.zmaps[b], H.zp[b], H.stream)); }
     else CUDA_TRY(launch_zsweep_simple(H.D[b], S, H.stream));
+    if (H.stats_on && !first) { CUDA_TRY(launch_stats(H.D[0], H.stats, H.stream)); H.stats_count += 1; }   // rms_add, df.cpp:606
     CUDA_TRY(cudaEventRecord(H.ev_free[b], H.stream));
     if (H.timing) CUDA_TRY(cudaEventRecord(H.ev[3], H.stream));
     H.step += 1;
@@ -826,6 +832,57 @@ int dfb_measure_fp64_peak(int device, double* tflops, double* sm_mhz_est) {
         *tflops = 2.0 * fma / (best * 1e-3) / 1e12;
         if (sm_mhz_est) *sm_mhz_est = fma / (best * 1e-3) / (prop.multiProcessorCount * 64.0) / 1e6;   // if 64 DFMA/clk/SM
         cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(d);
+    });
+}
+
+int dfb_stats_enable(dfb_handle h, int on) {
+    if (!h) return fail(DFB_ERR_ARG, "handle is NULL");
+    return guarded([&] {
+        CUDA_TRY(cudaSetDevice(h->device));
+        const size_t n = (size_t)h->D[0].Ny * h->D[0].W;
+        if (on && !h->stats) h->stats = h->dalloc<double>(6 * n);
+        if (on) { CUDA_TRY(cudaMemsetAsync(h->stats, 0, 6 * n * sizeof(double), h->stream)); h->stats_count = 0; }
+        h->stats_on = on != 0;             // off: keep what was accumulated, stop accumulating
+    });
+}
+
+int dfb_stats_get(dfb_handle h, int which, int as_rms, double* dst, int64_t* count) {
+    if (!h || which < 0 || which > 5) return fail(DFB_ERR_ARG, "bad argument");
+    if (!h->stats) return fail(DFB_ERR_STATE, "statistics are not enabled (dfb_stats_enable)");
+    return guarded([&] {
+        CUDA_TRY(cudaSetDevice(h->device));
+        const size_t n = (size_t)h->D[0].Ny * h->D[0].W;
+        if (dst) {
+            CUDA_TRY(cudaMemcpyAsync(dst, h->stats + (size_t)which * n, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            CUDA_TRY(cudaStreamSynchronize(h->stream));
+            if (as_rms && h->stats_count > 0 && which < 5)
+                for (size_t i = 0; i < n; ++i) dst[i] = std::sqrt(dst[i] / (double)h->stats_count);   // plot_rms, df.cpp:615-620
+        }
+        if (count) *count = h->stats_count;
+    });
+}
+
+// write_csv (df.cpp:764-803), opt-in: header, fixed notation with 15 decimals, one row per cell
+int dfb_write_csv(dfb_handle h, const char* path) {
+    if (!h || !path) return fail(DFB_ERR_ARG, "bad argument");
+    return guarded([&] {
+        CUDA_TRY(cudaSetDevice(h->device));
+        const int Ny = h->D[0].Ny, W = h->D[0].W;
+        const size_t n = (size_t)Ny * W;
+        std::vector<double> buf(5 * n);
+        for (int i = 0; i < 5; ++i)
+            CUDA_TRY(cudaMemcpyAsync(buf.data() + (size_t)i * n, field_ptr(*h, i), n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        FILE* fp = std::fopen(path, "w");
+        if (!fp) throw Error{DFB_ERR_IO, std::string("Error: cannot open ") + path + " for writing. (df.cpp:766-769)"};
+        std::fputs("z,y,u_fluc,v_fluc,w_fluc,T_fluc,rho_fluc\n", fp);
+        for (int j = 0; j < Ny; ++j)
+            for (int k = 0; k < W; ++k) {
+                const size_t c = (size_t)j * W + k;
+                std::fprintf(fp, "%.15f,%.15f,%.15f,%.15f,%.15f,%.15f,%.15f\n", h->plan.csv_zc[h->plan.k0 + k], h->plan.csv_yc[j],
+                             buf[c], buf[n + c], buf[2 * n + c], buf[3 * n + c], buf[4 * n + c]);
+            }
+        std::fclose(fp);
     });
 }
 

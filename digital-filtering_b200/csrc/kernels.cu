@@ -606,6 +606,27 @@ __global__ void __launch_bounds__(128) zsweep_epilogue_kernel(const __grid_const
 }
 
 // =================================================================================================
+// N2: running sums of squares (rms_add, df.cpp:571-582) + u'v', opt-in.  mul then add, like the reference.
+// =================================================================================================
+__global__ void __launch_bounds__(256) stats_kernel(const PlaneDev D, double* __restrict__ sums, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double u = D.f[0].fluc[i], v = D.f[1].fluc[i], w = D.f[2].fluc[i], T = D.T_fluc[i], r = D.rho_fluc[i];
+    sums[i] = __dadd_rn(sums[i], __dmul_rn(u, u));
+    sums[n + i] = __dadd_rn(sums[n + i], __dmul_rn(v, v));
+    sums[2 * n + i] = __dadd_rn(sums[2 * n + i], __dmul_rn(w, w));
+    sums[3 * n + i] = __dadd_rn(sums[3 * n + i], __dmul_rn(T, T));
+    sums[4 * n + i] = __dadd_rn(sums[4 * n + i], __dmul_rn(r, r));
+    sums[5 * n + i] = __dadd_rn(sums[5 * n + i], __dmul_rn(u, v));
+}
+
+cudaError_t launch_stats(const PlaneDev& D, double* sums, cudaStream_t st) {
+    const size_t n = (size_t)D.Ny * D.W;
+    stats_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(D, sums, n);
+    return cudaGetLastError();
+}
+
+// =================================================================================================
 // fp64 roofline denominator: dependent-chain-free DFMA issue, 8 chains per thread
 // =================================================================================================
 __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double a, double b) {

@@ -36,6 +36,7 @@ struct Plan {
     double d_i = 0, d_v = 0, U_e = 0, rho_e = 0, mu = 0, gcon = 287.0;
     double u_tau = 0, tau_w = 0;
     std::vector<double> yc_row, dy_row;          // first column of the geometry (ydline*d_i, df.cpp:115-116)
+    std::vector<double> csv_yc, csv_zc;          // cell-centre coordinates as write_csv prints them (df.cpp:785-786): [Ny], [NzG]
     std::vector<double> rows;                    // [8][Ny] R11,R21,R22,R33,Us,Ts,rhos,Ms
     FieldPlan f[3];
     CoefTable coef;

@@ -141,11 +141,36 @@ void build_plan(const dfb_config& cfg, Plan& P) {
         std::string line_path = cstr(cfg.line_file, cfg.line_file_len);
         if (line_path.empty()) line_path = "../line.dat";          // df.cpp:16
         int N_in = 0;
-        auto rst = read_zone_file(rst_path, N_in);
-        std::vector<double> yin_d(N_in), urms(N_in), vrms(N_in), wrms(N_in), uv(N_in);
-        for (int i = 0; i < N_in; ++i) {
-            if (rst[i].size() < 6) throw Error{DFB_ERR_IO, "'" + rst_path + "': fewer than 6 columns"};
-            yin_d[i] = rst[i][1]; urms[i] = rst[i][2]; vrms[i] = rst[i][3]; wrms[i] = rst[i][4]; uv[i] = rst[i][5];   // :270-275
+        std::vector<double> yin_d, urms, vrms, wrms, uv;
+        if (cfg.vel_file_offset > 0) {
+            // The DNS statistics file itself (M6Tw025_Stat.dat layout), as the Fortran caller configures it
+            // (fortran-main.f90:17-19: vel_file_offset = 142 header lines, vel_file_N_values = 330 rows).  Column
+            // choice as in the reference's preprocessor RST.cpp:43-50: y/delta = col 1, urms = 8, "v" (wall-normal)
+            // = col 10, "w" = col 9, u'v' = col 15.
+            std::ifstream fin(rst_path);
+            if (!fin) throw Error{DFB_ERR_IO, "cannot open input file '" + rst_path + "' (df.f90:327-330)"};
+            std::string line;
+            for (int i = 0; i < cfg.vel_file_offset; ++i) std::getline(fin, line);
+            while (std::getline(fin, line)) {
+                if (line.empty()) continue;
+                std::istringstream iss(line);
+                std::vector<double> v;
+                double x;
+                while (iss >> x) v.push_back(x);
+                if (v.size() > 15) {
+                    yin_d.push_back(v[1]); urms.push_back(v[8]); vrms.push_back(v[10]); wrms.push_back(v[9]); uv.push_back(v[15]);
+                    if (cfg.vel_file_N_values > 0 && (int)yin_d.size() >= cfg.vel_file_N_values) break;
+                }
+            }
+            N_in = (int)yin_d.size();
+            if (N_in < 2) throw Error{DFB_ERR_INTERP, "Need at least two data points to interpolate. (" + rst_path + ")"};
+        } else {
+            auto rst = read_zone_file(rst_path, N_in);
+            yin_d.resize(N_in); urms.resize(N_in); vrms.resize(N_in); wrms.resize(N_in); uv.resize(N_in);
+            for (int i = 0; i < N_in; ++i) {
+                if (rst[i].size() < 6) throw Error{DFB_ERR_IO, "'" + rst_path + "': fewer than 6 columns"};
+                yin_d[i] = rst[i][1]; urms[i] = rst[i][2]; vrms[i] = rst[i][3]; wrms[i] = rst[i][4]; uv[i] = rst[i][5];   // :270-275
+            }
         }
         // trim Ny to the rows inside the DNS data, df.cpp:282-288
         int new_Ny = 0;
@@ -197,6 +222,27 @@ void build_plan(const dfb_config& cfg, Plan& P) {
     for (int j = 0; j < Ny; ++j) {
         P.yc_row[j] = yc.empty() ? 0.0 : yc[(size_t)j * gstride];
         P.dy_row[j] = dy.empty() ? 0.0 : dy[(size_t)j * gstride];
+    }
+
+    // ---- cell-centre coordinates for the opt-in CSV writer (write_csv, df.cpp:776-786) ----
+    P.csv_yc.resize(Ny); P.csv_zc.resize(NzG);
+    if (default_grid) {
+        // the reference averages the four corner vertices; y = the tanh grid, z[...] = k * 0.000133 (df.cpp:99-100)
+        std::vector<double> yv(561);
+        double y_max = 3 * d_i, a = 2.0;
+        for (int j = 560; j >= 0; --j) {
+            double eta = ((j) * y_max / (560 + 1)) / y_max;
+            yv[std::abs(j - 560)] = y_max * (1 - std::tanh(a * eta) / std::tanh(a));
+        }
+        for (int j = 0; j < Ny; ++j) P.csv_yc[j] = 0.25 * (yv[j] + yv[j] + yv[j + 1] + yv[j + 1]);        // df.cpp:785 (n00,n01,n10,n11)
+        for (int k = 0; k < NzG; ++k) P.csv_zc[k] = 0.25 * (k * 0.000133 + (k + 1) * 0.000133 + k * 0.000133 + (k + 1) * 0.000133);   // df.cpp:786
+    } else {
+        for (int j = 0; j < Ny; ++j) P.csv_yc[j] = yc.empty() ? 0.0 : yc[(size_t)j * gstride];
+        double zacc = 0.0;
+        for (int k = 0; k < NzG; ++k) {
+            const double w = dz.empty() ? 1.0 : (per_row ? dz[0] : dz[k]);
+            P.csv_zc[k] = zacc + 0.5 * w; zacc += w;
+        }
     }
 
     // ---- slab ----

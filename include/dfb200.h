@@ -56,7 +56,8 @@ typedef struct dfb_config {
     double rho_e;               /* freestream density                   df.hpp:40 */
     double U_e;                 /* freestream velocity                  df.hpp:41 */
     double mu_e;                /* freestream viscosity                 df.hpp:42 */
-    int vel_file_offset;        /* header lines of the fluctuation file df.hpp:44 */
+    int vel_file_offset;        /* header lines of the fluctuation file df.hpp:44; > 0 selects the DNS statistics layout
+                                   (M6Tw025_Stat.dat: columns 1,8,10,9,15 as in RST.cpp:43-50), 0 the RST.dat layout */
     int vel_file_N_values;      /* data rows of the fluctuation file    df.hpp:45 */
     const char* grid_file;      /* df.hpp:47 (unused by the reference, kept for layout parity) */
     int grid_file_len;          /* <0: NUL-terminated; >=0: Fortran len_trim */
@@ -141,6 +142,16 @@ int dfb_generate_noise(dfb_handle h, int64_t step);
 /* checkpoint: filt_old[3][Ny*Nz] + step counter; the seed is in the config */
 int dfb_get_state(dfb_handle h, double* filt_old3, int64_t* step);
 int dfb_set_state(dfb_handle h, const double* filt_old3, int64_t step);
+
+/* N2 -- running statistics, the reference's only validation tool (rms_add / plot_rms, df.cpp:571-621), on the device
+ * and opt-in: after dfb_stats_enable(h, 1) every dfb_filter also accumulates per cell the sums of u'^2, v'^2, w'^2,
+ * T'^2, rho'^2 and u'v' (which = 0..5).  dfb_stats_get copies one of them to the host (as_rms != 0: sqrt(sum/count)
+ * like plot_rms, not for u'v') and returns the number of accumulated steps. */
+int dfb_stats_enable(dfb_handle h, int on);
+int dfb_stats_get(dfb_handle h, int which, int as_rms, double* dst, int64_t* count);
+/* N4 -- write_csv (df.cpp:764-803), opt-in and never called by dfb_filter: "z,y,u_fluc,v_fluc,w_fluc,T_fluc,rho_fluc",
+ * fixed notation, 15 decimals, one row per cell in j-major order. */
+int dfb_write_csv(dfb_handle h, const char* path);
 
 /* CUDA-event time of the last dfb_filter, ms: stage 0 noise, 1 y-sweep, 2 z-sweep+epilogue, 3 whole step.
  * Only recorded when enabled with dfb_set_timing(h, 1). */

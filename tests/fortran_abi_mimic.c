@@ -29,7 +29,7 @@ int main(int argc, char** argv) {
     dfb_config c;
     if (dfb_config_init(&c) != DFB_OK) return 3;
     c.d_i = 0.0013; c.rho_e = 0.044; c.U_e = 869.1; c.mu_e = 7.1212e-6;      /* fortran-main.f90:12-15 (mu: df.cpp:10) */
-    c.vel_file_offset = 142; c.vel_file_N_values = 330;                    /* fortran-main.f90:18-19 */
+    c.vel_file_offset = 0; c.vel_file_N_values = 330;       /* RST.dat layout (fortran-main.f90:18-19 uses 142/330 with the Stat file) */
     c.honor_flow_config = 1;
     c.grid_file = grid_file;         c.grid_file_len = len_trim(grid_file, 256);
     c.vel_fluc_file = vel_fluc_file; c.vel_fluc_file_len = len_trim(vel_fluc_file, 256);

@@ -228,6 +228,28 @@ def test_inject_mode_requires_noise(dfb, W):
     df.close()
 
 
+def test_dns_statistics_file_layout(dfb, O, tmp_path):
+    """N1: the Fortran caller's configuration (vel_file_offset = 142 header lines + the DNS statistics
+    layout, fortran-main.f90:17-19) gives the same tables as the preprocessed RST.dat (RST.cpp:43-50)."""
+    if not O.have_ref():
+        pytest.skip("needs the data files under oracle/_ref")
+    rst = [ln.split() for ln in open(O.RST_DAT).read().splitlines()[2:] if ln.strip()]
+    stat = tmp_path / "Stat.dat"
+    with open(stat, "w") as fh:
+        for i in range(142):
+            fh.write("# header line %d\n" % i)
+        for r in rst:
+            cols = ["0"] * 20
+            cols[0], cols[1], cols[8], cols[10], cols[9], cols[15] = r[0], r[1], r[2], r[3], r[4], r[5]
+            fh.write(" ".join(cols) + "\n")
+    a = dfb.DIGITAL_FILTER(dfb.DFConfig(vel_fluc_file=O.RST_DAT, line_file=O.LINE_DAT, seed=1))
+    b = dfb.DIGITAL_FILTER(dfb.DFConfig(vel_fluc_file=str(stat), line_file=O.LINE_DAT, seed=1, vel_file_offset=142, vel_file_N_values=330))
+    assert (a.Ny, a.Nz) == (b.Ny, b.Nz) == (510, 400)
+    assert np.array_equal(a.rows(), b.rows())
+    assert np.array_equal(a.u.fluc, b.u.fluc)
+    a.close(); b.close()
+
+
 def test_missing_file_is_an_io_status(dfb):
     with pytest.raises(dfb.DfbError) as e:
         dfb.DIGITAL_FILTER(dfb.DFConfig(vel_fluc_file="/nonexistent/RST.dat"))
@@ -296,3 +318,54 @@ def test_G3_reynolds_stresses_recovered(dfb, W):
         got = (float(np.median(rel)), float(np.percentile(rel, 95)), float(rel.max()))
         assert got[0] < lim[0] and got[1] < lim[1] and got[2] < lim[2], (name, got)
     df.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# "next" rows: N2 running statistics, N4 CSV writer
+# ---------------------------------------------------------------------------------------------
+def test_N2_running_statistics_match_rms_add(dfb, W):
+    """rms_add / plot_rms (df.cpp:571-621) on the device: per-cell sums of squares accumulated step by step
+    equal the same accumulation done on the host from the fetched fields, bit for bit."""
+    plane = W.plane_profile(40, 96, 8, 6)
+    df = dfb.DIGITAL_FILTER(dfb.DFConfig.from_plane(plane, seed=4))
+    df.stats_enable(True)
+    acc = np.zeros((6, 40, 96))
+    for _ in range(7):
+        df.filter(3e-7)
+        f = [df.u.fluc, df.v.fluc, df.w.fluc, df.T_fluc, df.rho_fluc]
+        for i in range(5):
+            acc[i] += f[i] * f[i]
+        acc[5] += f[0] * f[1]
+    for i in range(6):
+        got, cnt = df.stats(i)
+        assert cnt == 7 and np.array_equal(got, acc[i]), i
+    rms, _ = df.stats(0, rms=True)
+    assert np.array_equal(rms, np.sqrt(acc[0] / 7))
+    df.close()
+
+
+def test_N4_csv_matches_reference_writer(dfb, O, tmp_path):
+    """write_csv (df.cpp:764-803): same header, same fixed 15-decimal format, same coordinates and (within the
+    fp64 gate) the same numbers as the file the reference's own filter() call writes."""
+    if not O.have_ref():
+        pytest.skip("oracle/_ref did not travel")
+    ref = O.RefFilter()
+    df = dfb.DIGITAL_FILTER(dfb.DFConfig(vel_fluc_file=O.RST_DAT, line_file=O.LINE_DAT, noise_mode=dfb.NOISE_INJECT))
+    fo = ref.outputs()["filt_old"].copy()
+    ref.filter(1e-5)                                   # writes <run>/../files/cpp_vel_fluc.csv (df.cpp:466-467)
+    df.set_state(fo, 1)
+    for f in range(3):
+        df.set_noise_ref_layout(f, ref.fvec(f, "r_ys"), ref.fvec(f, "r_zs"))
+    df.filter(1e-5)
+    mine = tmp_path / "b200_vel_fluc.csv"
+    df.write_csv(mine)
+    a = open(os.path.join(O.REF_FILES, "cpp_vel_fluc.csv")).read().splitlines()
+    b = open(mine).read().splitlines()
+    assert a[0] == b[0] == "z,y,u_fluc,v_fluc,w_fluc,T_fluc,rho_fluc" and len(a) == len(b) == 1 + 510 * 400
+    for la, lb in list(zip(a[1:], b[1:]))[::997]:
+        ta, tb = la.split(","), lb.split(",")
+        assert ta[:2] == tb[:2]                        # coordinates print identically
+        assert all(len(x.split(".")[1]) == 15 for x in tb)
+        for x, y in zip(ta[2:], tb[2:]):
+            assert abs(float(x) - float(y)) <= 1e-12 * max(abs(float(x)), 1.0) + 2e-15
+    df.close(); ref.close()
