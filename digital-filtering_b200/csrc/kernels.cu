@@ -197,6 +197,9 @@ __global__ void __launch_bounds__(160, 3) ysweep_tma_kernel(const __grid_constan
         if (blockIdx.x == 0 && P.zcounter) *P.zcounter = 0;      // the z-sweep that follows pulls its items from here
     }
     __syncthreads();
+    // Programmatic dependent launch: everything above overlapped the previous kernel's tail; from here on we touch
+    // global data it may have produced (noise) or still read.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     if (warp == Y_G) {
         if (lane == 0) {
@@ -365,6 +368,9 @@ __global__ void __launch_bounds__(128) zsweep_epilogue_kernel(const __grid_const
     uint64_t* bars = reinterpret_cast<uint64_t*>(tail) + warp * 2;
     int* descs = reinterpret_cast<int*>(tail + 64) + warp * 16;              // [2][8]
     if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+    // Programmatic dependent launch: this CTA became resident while the y-sweep's last tiles were still running;
+    // wait for that grid to complete (and its writes to r_zs to be visible) before the first unit is claimed/staged.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     const long long tstart = (P.debug & 16) ? clock64() : 0;
     // claim the first two units; stage the first
@@ -681,9 +687,19 @@ cudaError_t ysweep_prepare() {
                                 cudaSharedmemCarveoutMaxShared);
 }
 
+static cudaLaunchConfig_t pdl_config(unsigned grid, unsigned block, size_t smem, cudaStream_t st, cudaLaunchAttribute* attr) {
+    attr->id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr->val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cfg;
+}
+
 cudaError_t launch_ysweep_tma(const YMaps& maps, const YParams& P, int n_tiles, cudaStream_t st) {
-    ysweep_tma_kernel<Y_RC, Y_NS><<<(unsigned)n_tiles, 160, sizeof(YSmem<Y_RC, Y_NS>), st>>>(maps, P);
-    return cudaGetLastError();
+    cudaLaunchAttribute attr;
+    cudaLaunchConfig_t cfg = pdl_config((unsigned)n_tiles, 160, sizeof(YSmem<Y_RC, Y_NS>), st, &attr);
+    return cudaLaunchKernelEx(&cfg, ysweep_tma_kernel<Y_RC, Y_NS>, maps, P);
 }
 
 static const void* zsweep_fn(int zk) { return zk == 16 ? (const void*)zsweep_epilogue_kernel<16> : (const void*)zsweep_epilogue_kernel<8>; }
@@ -698,9 +714,10 @@ cudaError_t zsweep_prepare(int zk, size_t smem, int* blocks_per_sm) {
 }
 
 cudaError_t launch_zsweep_tuned(const ZMaps& maps, const ZParams& P, cudaStream_t st) {
-    if (P.zk == 16) zsweep_epilogue_kernel<16><<<(unsigned)P.nblocks, 128, P.smem_bytes, st>>>(maps, P);
-    else zsweep_epilogue_kernel<8><<<(unsigned)P.nblocks, 128, P.smem_bytes, st>>>(maps, P);
-    return cudaGetLastError();
+    cudaLaunchAttribute attr;
+    cudaLaunchConfig_t cfg = pdl_config((unsigned)P.nblocks, 128, (size_t)P.smem_bytes, st, &attr);
+    if (P.zk == 16) return cudaLaunchKernelEx(&cfg, zsweep_epilogue_kernel<16>, maps, P);
+    return cudaLaunchKernelEx(&cfg, zsweep_epilogue_kernel<8>, maps, P);
 }
 
 cudaError_t launch_dfma_peak(double* out, int blocks, int iters, cudaStream_t st) {
