@@ -369,3 +369,97 @@ def test_N4_csv_matches_reference_writer(dfb, O, tmp_path):
         for x, y in zip(ta[2:], tb[2:]):
             assert abs(float(x) - float(y)) <= 1e-12 * max(abs(float(x)), 1.0) + 2e-15
     df.close(); ref.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# edge cases: explicit (odd, zero, large) half-widths, awkward shapes, batch call
+# ---------------------------------------------------------------------------------------------
+def _explicit_plane(W, Ny, Nz, Ny_rows, Nz_rows):
+    """row-uniform plane whose half-widths are SUPPLIED (dfb_config.N_y / N_z) instead of derived from geometry"""
+    yc = (np.arange(Ny) + 0.5) * 1e-5
+    N_y = np.stack([np.repeat(np.asarray(Ny_rows[f], dtype=np.int32)[:, None], Nz, axis=1) for f in range(3)])
+    N_z = np.stack([np.repeat(np.asarray(Nz_rows[f], dtype=np.int32)[:, None], Nz, axis=1) for f in range(3)])
+    return dict(name=f"explicit_{Ny}x{Nz}", Ny=Ny, Nz=Nz, d_i=W.D_I, U_e=W.U_E, yc=yc, dy=np.full(Ny, 1e-5), dz=np.full(Ny, 1e-5),
+                rows=W.synthetic_rows(yc + 1e-4), scales=W._scales(W.D_I), explicit_N=True,
+                N_y=N_y, N_z=N_z, Ny_max=[int(N_y[f].max()) for f in range(3)], Nz_max=[int(N_z[f].max()) for f in range(3)])
+
+
+def _run_explicit(dfb, O, plane, seed, dts, variant=0):
+    Ny, Nz = plane["Ny"], plane["Nz"]
+    cfg = dfb.DFConfig.from_plane(plane, noise_mode=dfb.NOISE_INJECT, kernel_variant=variant)
+    cfg.geom_per_row = 0                       # N arrays are per cell
+    cfg.yc = cfg.dy = cfg.dz = None
+    cfg.N_y, cfg.N_z = plane["N_y"], plane["N_z"]
+    df = dfb.DIGITAL_FILTER(cfg)
+    fo = np.zeros((3, Ny, Nz))
+    for s, dt in enumerate([0.0] + list(dts)):
+        rys = [O.noise_rys(seed, 0, f, s, Ny, plane["Ny_max"][f], Nz) for f in range(3)]
+        hal = [O.noise_halo(seed, 0, f, s, Ny, plane["Nz_max"][f]) if plane["Nz_max"][f] else np.zeros((Ny, 0)) for f in range(3)]
+        for f in range(3):
+            df.set_noise(f, rys[f], hal[f] if plane["Nz_max"][f] else None)
+        df.first_step() if s == 0 else df.filter(dt)
+        df.fetch()
+        o = O.step(plane, rys, hal, fo, dt, first_step=(s == 0))
+        fo = o["filt_old"]
+        for f, F in enumerate((df.u, df.v, df.w)):
+            ok, r = normwise_close(F.fluc, o["fluc"][f], TOL)
+            assert ok, (plane["name"], s, f, r)
+        if s:
+            assert normwise_close(df.T_fluc, o["T"], TOL)[0] and normwise_close(df.rho_fluc, o["rho"], TOL)[0]
+    tuned = df.tuned
+    df.close()
+    return tuned
+
+
+def test_explicit_odd_and_mixed_half_widths(dfb, O, W):
+    rng = np.random.default_rng(5)
+    Ny, Nz = 37, 530
+    Nyr = [rng.integers(1, 40, Ny) for _ in range(3)]            # odd and even, changing every row
+    Nzr = [rng.integers(1, 23, Ny) for _ in range(3)]
+    plane = _explicit_plane(W, Ny, Nz, Nyr, Nzr)
+    assert _run_explicit(dfb, O, plane, seed=12, dts=[3e-7])     # row-uniform -> tuned kernels, scalar z staging (odd N)
+
+
+def test_large_half_widths_beyond_128(dfb, O, W):
+    Ny, Nz = 24, 700
+    Nyr = [np.full(Ny, 200), np.full(Ny, 96), np.linspace(20, 260, Ny).astype(int) // 2 * 2]
+    Nzr = [np.full(Ny, 300), np.full(Ny, 2), np.full(Ny, 130)]
+    plane = _explicit_plane(W, Ny, Nz, Nyr, Nzr)
+    assert _run_explicit(dfb, O, plane, seed=13, dts=[3e-7])
+
+
+@pytest.mark.parametrize("shape", [(3, 5), (9, 17), (8, 16), (65, 1)])
+def test_tiny_and_awkward_shapes(dfb, O, W, shape):
+    Ny, Nz = shape
+    Nyr = [np.full(Ny, 2), np.full(Ny, 4), np.full(Ny, 2)]
+    Nzr = [np.full(Ny, 2), np.full(Ny, 2), np.full(Ny, 4)]
+    plane = _explicit_plane(W, Ny, Nz, Nyr, Nzr)
+    _run_explicit(dfb, O, plane, seed=14, dts=[2e-7, 2e-7])
+
+
+def test_filter_batch_matches_step_by_step(dfb, W):
+    plane = W.plane_profile(40, 64, 8, 6)
+    a = dfb.DIGITAL_FILTER(dfb.DFConfig.from_plane(plane, seed=21))
+    b = dfb.DIGITAL_FILTER(dfb.DFConfig.from_plane(plane, seed=21), fetch=False)
+    dts = np.array([1e-7, 2e-7, 3e-7, 1e-7])
+    out = np.zeros((4, 5, 40, 64))
+    b.filter_batch(dts, out)
+    for s, dt in enumerate(dts):
+        a.filter(float(dt))
+        for i, ref in enumerate((a.u.fluc, a.v.fluc, a.w.fluc, a.T_fluc, a.rho_fluc)):
+            assert np.array_equal(out[s, i], ref), (s, i)
+    a.close(); b.close()
+
+
+def test_timing_mode_does_not_change_results(dfb, W):
+    plane = W.plane_profile(40, 64, 8, 6)
+    a = dfb.DIGITAL_FILTER(dfb.DFConfig.from_plane(plane, seed=22))
+    b = dfb.DIGITAL_FILTER(dfb.DFConfig.from_plane(plane, seed=22))
+    b.set_timing(True)
+    for _ in range(3):
+        a.filter(1e-7); b.filter(1e-7)
+    b.set_timing(False)
+    a.filter(1e-7); b.filter(1e-7)
+    assert np.array_equal(a.u.fluc, b.u.fluc) and np.array_equal(a.rho_fluc, b.rho_fluc)
+    assert b.last_ms()["step"] > 0
+    a.close(); b.close()
