@@ -53,6 +53,7 @@ struct dfb_filter_s {
     uint64_t seed = 0;
     int plane_id = 0;
     int64_t step = 0;                 // steps completed (the constructor's first step counts as one)
+    int z_launches = 0;               // stamp of the z-sweep's u->v completion flags: never rewinds (dfb_set_state may rewind `step`)
     bool injected[3] = {false, false, false};
     cudaStream_t stream = nullptr;    // main stream (high priority): sweeps + epilogue
     cudaStream_t side = nullptr;      // low-priority stream: next step's noise, generated while this step filters
@@ -456,7 +457,7 @@ void run_step(dfb_filter_s& H, double dt, bool first) {
         S.sa[f] = std::sqrt(alpha);                                // df.cpp:415
         S.sb[f] = std::sqrt(1.0 - alpha);
     }
-    if (H.tuned) { H.zp[b].S = S; H.zp[b].stamp = (int)(H.step + 1); CUDA_TRY(launch_zsweep_tuned(H.zmaps[b], H.zp[b], H.stream)); }
+    if (H.tuned) { H.zp[b].S = S; H.zp[b].stamp = ++H.z_launches; CUDA_TRY(launch_zsweep_tuned(H.zmaps[b], H.zp[b], H.stream)); }
     else CUDA_TRY(launch_zsweep_simple(H.D[b], S, H.stream));
     if (H.stats_on && !first) { CUDA_TRY(launch_stats(H.D[0], H.stats, H.stream)); H.stats_count += 1; }   // rms_add, df.cpp:606
     CUDA_TRY(cudaEventRecord(H.ev_free[b], H.stream));

@@ -217,6 +217,11 @@ def test_checkpoint_resume(dfb, W):
     b.set_state(fo, step)
     b.filter(2e-7)
     assert step == 4 and np.array_equal(a.u.fluc, b.u.fluc) and np.array_equal(a.rho_fluc, b.rho_fluc)
+    # rewinding the SAME handle to the step it just finished must not see stale u->v completion stamps
+    keep_v = a.v.fluc.copy()
+    a.set_state(fo, step)
+    a.filter(2e-7)
+    assert np.array_equal(a.v.fluc, keep_v)
     a.close(); b.close()
 
 
