@@ -321,6 +321,39 @@ def run_b200(args, plane):
         except Exception as e:   # the checker is optional for the bench; say so rather than die
             cpu = dict(value=None, unit="cell-updates/s", cores=0, kind="unavailable", sample=str(e)[:200])
 
+    # ---- the other single-GPU configurations of BASELINE.json, briefly (parity-test cases; reported for context) ----
+    sweep = None
+    if world == 1 and not args.no_sweep:
+        from digital_filtering_b200 import workloads as WL
+        sweep = {}
+        cases = [("1024x2048_saturated_N128", lambda: dfb.DFConfig.from_plane(WL.NAMED["1024x2048_saturated_N128"](), seed=1, device=local)),
+                 ("512x512_N32", lambda: dfb.DFConfig.from_plane(WL.NAMED["512x512_N32"](), seed=1, device=local))]
+        rst, ln = os.path.join(ROOT, "oracle", "_ref", "files", "RST.dat"), os.path.join(ROOT, "oracle", "_ref", "line.dat")
+        if os.path.exists(rst) and os.path.exists(ln):
+            cases.append(("reference_default_plane_510x400", lambda: dfb.DFConfig(vel_fluc_file=rst, line_file=ln, seed=1, device=local)))
+        for name, mk in cases:
+            try:
+                d2 = dfb.DIGITAL_FILTER(mk(), fetch=False)
+                st2 = torch.cuda.ExternalStream(d2.stream(), device=local)
+                for _ in range(5):
+                    d2.filter(DT)
+                d2.sync()
+                n2 = 200
+                a2, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a2.record(st2)
+                for _ in range(n2):
+                    d2.filter(DT)
+                b2.record(st2)
+                d2.sync()
+                ms2 = a2.elapsed_time(b2) / n2
+                taps2 = d2.taps_per_step
+                sweep[name] = dict(cells=d2.n_cells, ms_per_step=ms2, cell_updates_per_s=d2.n_cells / (ms2 * 1e-3),
+                                   step_tflops=2 * taps2 / (ms2 * 1e-3) / 1e12, step_frac_fp64=2 * taps2 / (ms2 * 1e-3) / 1e12 / fp64_peak,
+                                   l2_note="back-to-back steps, no flush (context only)")
+                d2.close()
+            except Exception as e:
+                sweep[name] = dict(error=str(e)[:160])
+
     line = dict(metric=METRIC, value=value, unit="cell-updates/s", n_gpus=world, steps=K, warmup=Wm, ms_per_step=step_ms,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
                 config=dict(workload=plane["name"], plane=[plane["Ny"], plane["Nz"]], max_half_width=[int(max(a.max() for a in N_y)), int(max(a.max() for a in N_z))],
@@ -330,7 +363,7 @@ def run_b200(args, plane):
                 clocks=clocks, gpu_launches=3 * K, wall_ms_per_step=1e3 * t_wall / K,
                 e2e=dict(value=e2e_value, unit="cell-updates/s", h2d_bytes_per_step=8, d2h_bytes_per_step=40 * cells,
                          call="dfb_filter_to_host (filter(dt) + u',v',w',T',rho' into pinned host arrays); input is the scalar dt"),
-                roofline=roofline, cpu_baseline=cpu)
+                roofline=roofline, cpu_baseline=cpu, other_configs=sweep)
     print(json.dumps(line), flush=True)
     df.close()
     if dist is not None:
@@ -345,6 +378,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the brief runs of the other named configurations")
     args = ap.parse_args()
     import _dfb_import  # noqa: F401
     from digital_filtering_b200 import workloads as W
