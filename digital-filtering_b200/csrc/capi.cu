@@ -79,6 +79,7 @@ struct dfb_filter_s {
     // noise
     std::vector<NoiseHost> noise;
     NoiseParams np{};
+    unsigned long long* tl = nullptr; // development aid (DFB_TIMELINE): 64 steps x {noise, y, z} x {start, end}
     // N2: running statistics (opt-in)
     double* stats = nullptr;          // [6][Ny*W]: sum u'^2, v'^2, w'^2, T'^2, rho'^2, u'v'
     int64_t stats_count = 0;
@@ -131,6 +132,8 @@ EncodeTiledFn encode_tiled() {
     }
     return fn;
 }
+
+void timeline_reset(dfb_filter_s& H);
 
 void build_device(dfb_filter_s& H) {
     const Plan& P = H.plan;
@@ -239,6 +242,7 @@ void build_device(dfb_filter_s& H) {
         H.yp[0].cmat = H.upload(cmat);
         H.yp[0].D = H.D[0];
         H.yp[0].prof = H.dalloc<unsigned long long>(8);
+        if (std::getenv("DFB_TIMELINE")) { H.tl = H.dalloc<unsigned long long>(512); timeline_reset(H); }
         H.yp[0].debug = std::getenv("DFB_DEBUG_Y") ? std::atoi(std::getenv("DFB_DEBUG_Y")) : 0;
         H.yp[1] = H.yp[0];
         H.yp[1].D = H.D[1];
@@ -261,7 +265,7 @@ void build_device(dfb_filter_s& H) {
         {
             // outputs per lane: 16 (fewest LDS per DFMA) unless the plane is narrower than one 512-column strip
             const char* zk_env = std::getenv("DFB_ZK");
-            const int ZKc = zk_env ? std::atoi(zk_env) : (W >= 384 ? 16 : 8);
+            const int ZKc = zk_env ? std::atoi(zk_env) : (P.NzG >= 384 ? 16 : 8);    // by the PLANE's width: slabs then share the plane's lane blocking
             if (ZKc != 8 && ZKc != 16) throw Error{DFB_ERR_ARG, "DFB_ZK must be 8 or 16"};
             const int strip = 32 * ZKc;
             Z.zk = ZKc;
@@ -276,12 +280,24 @@ void build_device(dfb_filter_s& H) {
                 if (!need[N]) continue;
                 const int d = ((-N) % ZKc + ZKc) % ZKc;
                 const int nchunk = 1 + (2 * N + d + ZKc - 1) / ZKc;
-                const int clen = round_up((nchunk + 1) * ZKc, 16);
+                const int clen = round_up((nchunk + 1) * ZKc, 16) + 16;     // + one 128-byte header line at the end (recursive form)
                 pptr[N] = (long long)pvals.size();
                 pvals.resize(pvals.size() + clen, 0.0);
                 double* B = pvals.data() + pptr[N];
                 const double* b = P.coef.vals.data() + P.coef.ptr[N];
                 for (int t = 0; t <= 2 * N; ++t) B[t + ZKc + d] = b[t];
+                if (N >= 1) {
+                    // b_i = a^|i| / s with a = exp(-2 pi / N) (df.cpp:168-177): the header carries what the recursive
+                    // evaluation needs: a, a^(N+1), 1/s, N, d.  a is the reference's own i = 1 weight: b_1 / b_0.
+                    double* hdr = B + clen - 16;
+                    const double a = std::exp(-2.0 * 3.14159265358979323846 * 1.0 / N);
+                    hdr[0] = a;
+                    hdr[1] = (double)std::pow((long double)a, (long double)(N + 1));
+                    hdr[2] = b[N];                    // centre coefficient = 1 / s
+                    hdr[3] = (double)N;
+                    hdr[4] = (double)d;
+                    for (int q = 1; q <= 4; ++q) hdr[4 + q] = (double)std::pow((long double)a, (long double)(1 << q));   // a^2, a^4, a^8, a^16
+                }
                 maxlines = std::max(maxlines, 32 + nchunk);          // lane 31 reads line 31 + ch, ch < nchunk
                 maxcoef = std::max(maxcoef, clen);
             }
@@ -307,7 +323,7 @@ void build_device(dfb_filter_s& H) {
                     ZUnit u{};
                     u.j = j; u.f = f;
                     u.nchunk = 1 + (2 * N + d + ZKc - 1) / ZKc;
-                    u.cbytes = round_up((u.nchunk + 1) * ZKc, 16) * (int)sizeof(double);
+                    u.cbytes = (round_up((u.nchunk + 1) * ZKc, 16) + 16) * (int)sizeof(double);
                     u.coff16 = (int)(pptr[N] / 16);
                     const FieldDev& F = H.D[0].f[f];
                     for (int si = 0; si < nstrips; ++si) {
@@ -322,10 +338,20 @@ void build_device(dfb_filter_s& H) {
             }
             Z.units = H.upload(units);
             Z.n_units = (int)units.size();
+            {
+                // Recursive evaluation of the truncated two-sided exponential (see the kernel) unless the slab starts or ends off a
+                // 16-column boundary of the plane (its lane blocks would differ from the whole plane's: results would agree to
+                // ~1e-14 but not bit for bit) or a row has N = 0.  DFB_Z_MODE=0 forces the direct Toeplitz form.
+                bool rec = (P.k0 % 16) == 0 && (P.k1 % 16 == 0 || P.k1 == P.NzG);
+                for (int f = 0; f < 3; ++f) for (int v : P.f[f].N_z_row) rec = rec && v >= 1;
+                const char* zm = std::getenv("DFB_Z_MODE");
+                Z.zmode = zm ? std::atoi(zm) : (rec ? 1 : 0);
+                if (Z.zmode == 1 && !rec) throw Error{DFB_ERR_ARG, "DFB_Z_MODE=1 needs slab boundaries on multiples of 16 columns and N_z >= 1"};
+            }
             Z.flags = H.dalloc<int>((size_t)Ny * nstrips);
             Z.counter = H.dalloc<int>(2);        // one work counter per buffer set: y(s+1) resets its own while z(s) still pulls from the other
             Z.debug = std::getenv("DFB_DEBUG_Z") ? std::atoi(std::getenv("DFB_DEBUG_Z")) : 0;
-            Z.prof = H.dalloc<unsigned long long>(8);
+            Z.prof = H.dalloc<unsigned long long>(4096);
             cudaDeviceProp prop;
             CUDA_TRY(cudaGetDeviceProperties(&prop, H.device));
             int zb = 1;
@@ -406,7 +432,7 @@ void build_device(dfb_filter_s& H) {
     for (int t = 0; t < max_np; ++t) slot[t] = pcg_jump(4u * (uint64_t)t, 1u);
     H.np.slot_jump = H.upload(slot);
     H.np.max_np = max_np;
-    H.np.chunks = (max_np + 127) / 128;
+    H.np.chunks = (max_np + noise_threads() - 1) / noise_threads();
     CUDA_TRY(cudaStreamSynchronize(H.stream));
 }
 
@@ -424,9 +450,20 @@ void fill_noise_params(dfb_filter_s& H, int64_t step) {
     H.np.n_arrays = n;
 }
 
+void timeline_reset(dfb_filter_s& H) {
+    std::vector<unsigned long long> init(512, 0ull);
+    for (int i = 0; i < 512; i += 2) init[i] = ~0ull;                  // starts: atomicMin
+    CUDA_TRY(cudaMemcpy(H.tl, init.data(), 512 * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+}
+
 void launch_noise_for(dfb_filter_s& H, int64_t step, int b, cudaStream_t st) {
     H.ybuf_step[b] = -1;                 // new noise invalidates whatever y-sweep result the set held
     fill_noise_params(H, step);
+    H.np.tl = H.tl ? H.tl + (step % 64) * 8 : nullptr;
+    {   // resident shape only for the look-ahead launch on the side stream (experiment: DFB_NOISE_CTAS)
+        const char* nc = std::getenv("DFB_NOISE_CTAS");
+        H.np.resident_ctas = (nc && st == H.side) ? std::atoi(nc) : 0;
+    }
     CUDA_TRY(launch_noise(H.np, H.D[b], st));
     CUDA_TRY(cudaEventRecord(H.ev_noise[b], st));
     H.buf_step[b] = step;
@@ -443,6 +480,7 @@ void run_step(dfb_filter_s& H, double dt, bool first) {
         throw Error{DFB_ERR_STATE, "noise_mode = inject: dfb_set_noise must be called for u, v and w before every step"};
     }
     H.noise_view = b;
+    if (H.tl) { H.yp[b].tl = H.tl + (H.step % 64) * 8 + 2; H.zp[b].tl = H.tl + (H.step % 64) * 8 + 4; }
     if (H.timing) CUDA_TRY(cudaEventRecord(H.ev[1], H.stream));
     if (H.noise_mode == DFB_NOISE_GENERATE && H.ybuf_step[b] == H.step) {
         // this step's y-sweep already ran (or is running) on the side stream; ev_noise[b] above covers it
@@ -554,7 +592,8 @@ int dfb_create(const dfb_config* cfg, dfb_handle* out) {
         int prio_lo = 0, prio_hi = 0;
         CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
         CUDA_TRY(cudaStreamCreateWithPriority(&H->stream, cudaStreamNonBlocking, prio_hi));
-        CUDA_TRY(cudaStreamCreateWithPriority(&H->side, cudaStreamNonBlocking, prio_lo));
+        const char* sp = std::getenv("DFB_SIDE_PRIO");          // experiment: 0 = lowest (default), 1 = same as the main stream
+        CUDA_TRY(cudaStreamCreateWithPriority(&H->side, cudaStreamNonBlocking, (sp && std::atoi(sp) == 1) ? prio_hi : prio_lo));
         for (auto& e2 : H->ev) CUDA_TRY(cudaEventCreate(&e2));
         for (int b = 0; b < 2; ++b) {
             CUDA_TRY(cudaEventCreateWithFlags(&H->ev_noise[b], cudaEventDisableTiming));
@@ -894,6 +933,30 @@ int dfb_debug_yprof(dfb_handle h, unsigned long long* out8) {
         if (!h->yp[0].prof) throw Error{DFB_ERR_STATE, "no profile buffer"};
         CUDA_TRY(cudaMemcpy(out8, h->yp[0].prof, 64, cudaMemcpyDeviceToHost));
         CUDA_TRY(cudaMemset(h->yp[0].prof, 0, 64));
+    });
+}
+
+int dfb_debug_timeline(dfb_handle h, unsigned long long* out512) {
+    // development aid: DFB_TIMELINE=1 at create; returns and clears 64 step slots x {noise, y, z, -} x {start, end} (ns)
+    if (!h || !out512) return fail(DFB_ERR_ARG, "bad argument");
+    return guarded([&] {
+        if (!h->tl) throw Error{DFB_ERR_STATE, "DFB_TIMELINE was not set when the handle was created"};
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->side));
+        CUDA_TRY(cudaMemcpy(out512, h->tl, 512 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        timeline_reset(*h);
+    });
+}
+
+int dfb_debug_ztrace(dfb_handle h, unsigned long long* out, int n) {
+    // development aid (DFB_DEBUG_Z & 64): per-unit clock64 stamps of the warps resident on SM 0
+    if (!h || !out || n > 4096) return fail(DFB_ERR_ARG, "bad argument");
+    return guarded([&] {
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        if (!h->zp[0].prof) throw Error{DFB_ERR_STATE, "no profile buffer"};
+        CUDA_TRY(cudaMemcpy(out, h->zp[0].prof, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemset(h->zp[0].prof, 0, sizeof(unsigned long long) * 4096));
+        CUDA_TRY(cudaMemset(h->zp[0].prof + 2048, 0xff, sizeof(unsigned long long) * 256));     // per-SM earliest start (atomicMin)
     });
 }
 

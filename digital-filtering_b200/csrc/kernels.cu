@@ -15,15 +15,26 @@
 #include "device.cuh"
 #include "kernels.hpp"
 
+#ifndef NOISE_THREADS
+#define NOISE_THREADS 128
+#endif
+
 namespace dfb {
+
+// development aid (DFB_TIMELINE): earliest start / latest end of a launch on the GPU's global timer
+__device__ __forceinline__ void tl_stamp(unsigned long long* tl, int end) {
+    if (!tl) return;
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    if (end) atomicMax(tl + 1, gt); else atomicMin(tl, gt);
+}
 
 // =================================================================================================
 // H1: white noise
 // =================================================================================================
-__global__ void __launch_bounds__(128) noise_kernel(const NoiseParams P, const PlaneDev D) {
-    const NoiseArray& A = P.a[blockIdx.z];
-    const int seg = blockIdx.y;
-    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void noise_block(const NoiseParams& P, const PlaneDev& D, int bx, int seg, int bz) {
+    const NoiseArray& A = P.a[bz];
+    const int slot = bx * NOISE_THREADS + threadIdx.x;
     if (seg >= A.n_seg) return;
     const int np = A.seg_np[seg];
     if (slot >= np) return;
@@ -63,6 +74,27 @@ __global__ void __launch_bounds__(128) noise_kernel(const NoiseParams P, const P
             if (c >= 0 && c < Wz) dst[c] = i ? z1 : z0;
         }
     }
+}
+
+// Two launch shapes.  Classic: one CTA per (128 pairs, segment, array).  Resident (P.resident_ctas > 0): a small grid of CTAs
+// (about one per SM) that walk the same blocks with a stride: launched when the previous step retires, they sit beside the
+// sweeps' CTAs for the whole step as the oldest warps of their SM sub-partitions, so the warp scheduler never starves them.
+__global__ void __launch_bounds__(NOISE_THREADS) noise_kernel(const NoiseParams P, const PlaneDev D) {
+    if (P.resident_ctas > 0) {
+        if (threadIdx.x == 0) tl_stamp(P.tl, 0);
+        const int nseg = P.max_seg;
+        const long long total = (long long)P.chunks * nseg * P.n_arrays;
+        for (long long v = blockIdx.x; v < total; v += gridDim.x) {
+            const int bx = (int)(v % P.chunks);
+            const long long r = v / P.chunks;
+            noise_block(P, D, bx, (int)(r % nseg), (int)(r / nseg));
+        }
+        if (threadIdx.x == 0) tl_stamp(P.tl, 1);
+        return;
+    }
+    if (threadIdx.x == 0 && (blockIdx.y & 31) == 0) tl_stamp(P.tl, 0);     // sampled: one row in 32 (same-address atomics)
+    noise_block(P, D, blockIdx.x, blockIdx.y, blockIdx.z);
+    if (threadIdx.x == 0 && (blockIdx.y & 31) == 0) tl_stamp(P.tl, 1);
 }
 
 // =================================================================================================
@@ -195,6 +227,7 @@ __global__ void __launch_bounds__(160, 3) ysweep_tma_kernel(const __grid_constan
         for (int s = 0; s < NS; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], Y_G); }
         mbar_fence_init();
         if (blockIdx.x == 0 && P.zcounter) *P.zcounter = 0;      // the z-sweep that follows pulls its items from here
+        tl_stamp(P.tl, 0);
     }
     __syncthreads();
     // Programmatic dependent launch: everything above overlapped the previous kernel's tail; from here on we touch
@@ -293,6 +326,7 @@ __global__ void __launch_bounds__(160, 3) ysweep_tma_kernel(const __grid_constan
             }
         }
     }
+    if (lane == 0) tl_stamp(P.tl, 1);
     if (P.debug && lane == 0) {
         const long long tend = clock64();
         atomicAdd(P.prof + 0, (unsigned long long)tw);                 // consumer waits on full barriers
@@ -372,7 +406,25 @@ __global__ void __launch_bounds__(128) zsweep_epilogue_kernel(const __grid_const
     // wait for that grid to complete (and its writes to r_zs to be visible) before the first unit is claimed/staged.
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
+    if (lane == 0) tl_stamp(P.tl, 0);
     const long long tstart = (P.debug & 16) ? clock64() : 0;
+    int trace_slot = -1;                                   // development aid (DFB_DEBUG_Z & 64): unit timeline of the warps on SM 0
+    unsigned smid = 0;
+    if (P.debug & 64) {
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        if (lane == 0) {
+            unsigned long long gt;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+            atomicMin(P.prof + 2048 + smid, gt);
+        }
+        if (smid == 0) {
+            int sl = 0;
+            if (lane == 0) sl = (int)atomicAdd(P.prof + 8, 1ull);
+            trace_slot = __shfl_sync(0xffffffffu, sl, 0);
+            if (trace_slot >= 15) trace_slot = -1;
+            if (trace_slot >= 0 && lane == 0) P.prof[16 + trace_slot * 256 + 255] = (unsigned long long)warp;
+        }
+    }
     // claim the first two units; stage the first
     int claim = 0;
     if (lane == 0) claim = atomicAdd(P.counter, 1);
@@ -410,7 +462,7 @@ __global__ void __launch_bounds__(128) zsweep_epilogue_kernel(const __grid_const
         const bool coalesced = (c0 + Z_STRIP <= D.W) && ((sbase & 1) == 0) && !(P.debug & 4);
         const FieldDev& F = D.f[f];
         const bool blend = !P.S.first_step;
-        const long long tunit = (P.debug & 16) ? clock64() : 0;
+        const long long tunit = (P.debug & (16 | 64)) ? clock64() : 0;
 
         // filt_old of this strip, coalesced (piece p = lane + 32 m): requested now, consumed after the tap loop
         double2 fo_pc[ZK / 2];
@@ -420,10 +472,91 @@ __global__ void __launch_bounds__(128) zsweep_epilogue_kernel(const __grid_const
         }
         const long long t0 = (P.debug & 16) ? clock64() : 0;
         mbar_wait(&bars[n & 1], (n >> 1) & 1);
-        const long long t1 = (P.debug & 16) ? clock64() : 0;
+        const long long t1 = (P.debug & (16 | 64)) ? clock64() : 0;
         unsigned char* cbuf = wbase + (size_t)(n & 1) * P.unit_bytes;
         const double* B = reinterpret_cast<const double*>(cbuf + P.box_bytes);
         double acc[ZK];
+        if (P.zmode == 1) {
+            // ---- recursive form ----
+            // The reference's coefficients are a truncated two-sided exponential, b_i = a^|i| / s, a = exp(-2 pi / N)
+            // (df.cpp:168-177), so with F_k = sum_{i=0..N} a^i x_{k-i} and B_k = sum_{i=0..N} a^i x_{k+i}
+            //     out_k = (F_k + B_k - x_k) / s,   F_k = a F_{k-1} + x_k - a^(N+1) x_{k-N-1},   B_k = a B_{k+1} + x_k - a^(N+1) x_{k+N+1}.
+            // Each lane starts its two recursions with a Horner pass over the N+1 samples before its first / after its last
+            // output (the same recurrence with nothing to drop), then walks its ZK outputs: ~2(N + 2 ZK) FMAs per lane instead of
+            // ZK (2N+1).  Lane blocks are anchored to plane columns (multiples of 16), so slabs reproduce the whole plane.
+            // Every operation is an explicit round-to-nearest intrinsic.  Agreement with the direct sum: ~1e-15 of the rms.
+            const double* hdr = reinterpret_cast<const double*>(cbuf + P.box_bytes + dcur[5]) - 16;
+            const double a = hdr[0], naN1 = -hdr[1], cn = hdr[2];
+            const int Nn = (int)hdr[3], dd = (int)hdr[4];
+            const int cl = (dd + Nn) / ZK;                 // the lane's own ZK samples are line cl of its window; cl >= 1
+            const int ef = (ZK - 1 + Nn) % ZK;             // last element used of the farthest line (line 2 cl)
+            auto load_line = [&](int m, double* x) {
+                const int line = lane + m;
+                const unsigned char* lp = cbuf + line * LB;
+                const int sw = swz(line) << 4;
+#pragma unroll
+                for (int i = 0; i < ZK / 2; ++i) {
+                    const double2 t = *reinterpret_cast<const double2*>(lp + ((i << 4) ^ sw));
+                    x[2 * i] = t.x; x[2 * i + 1] = t.y;
+                }
+            };
+            auto lds1 = [&](int p) {                       // sample p of the lane's window (p >= 0)
+                const int line = lane + p / ZK, e = p % ZK;
+                return *reinterpret_cast<const double*>(cbuf + line * LB + ((((e >> 1) ^ swz(line))) << 4) + (e & 1) * 8);
+            };
+            // Horner over whole lines as a binary tree: the line's ZK terms are folded pairwise with a, a^2, a^4, (a^8) -- independent
+            // of the running value -- and only one FMA per line, F <- a^ZK F + T, is on the dependent chain.
+            const double a2 = hdr[5], a4 = hdr[6], a8 = hdr[7], aZK = ZK == 16 ? hdr[8] : hdr[7];
+            double Fc = 0.0, Bc = 0.0;
+            for (int m = 0; m < cl; ++m) {
+                double xa[ZK], xb[ZK];
+                load_line(m, xa);                          // causal: oldest line first, element 0 oldest
+                load_line(2 * cl - m, xb);                 // anti-causal: farthest line first, element ZK-1 farthest
+                if (m == 0) {
+#pragma unroll
+                    for (int e = 0; e < ZK; ++e) {         // outside the window: contributes nothing
+                        if (e < dd) xa[e] = 0.0;
+                        if (e > ef) xb[e] = 0.0;
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < ZK / 2; ++i) {
+                    xa[i] = __fma_rn(a, xa[2 * i], xa[2 * i + 1]);                     // newer element has the smaller power
+                    xb[i] = __fma_rn(a, xb[2 * i + 1], xb[2 * i]);
+                }
+#pragma unroll
+                for (int i = 0; i < ZK / 4; ++i) {
+                    xa[i] = __fma_rn(a2, xa[2 * i], xa[2 * i + 1]);
+                    xb[i] = __fma_rn(a2, xb[2 * i + 1], xb[2 * i]);
+                }
+#pragma unroll
+                for (int i = 0; i < ZK / 8; ++i) {
+                    xa[i] = __fma_rn(a4, xa[2 * i], xa[2 * i + 1]);
+                    xb[i] = __fma_rn(a4, xb[2 * i + 1], xb[2 * i]);
+                }
+                if (ZK == 16) {
+                    xa[0] = __fma_rn(a8, xa[0], xa[1]);
+                    xb[0] = __fma_rn(a8, xb[1], xb[0]);
+                }
+                Fc = __fma_rn(aZK, Fc, xa[0]);
+                Bc = __fma_rn(aZK, Bc, xb[0]);
+            }
+            double xc[ZK], Fv[ZK];
+            load_line(cl, xc);
+#pragma unroll
+            for (int kk = 0; kk < ZK; ++kk) {
+                Fc = __fma_rn(a, Fc, xc[kk]);
+                if (kk > 0) Fc = __fma_rn(naN1, lds1(dd + kk - 1), Fc);
+                Fv[kk] = Fc;
+            }
+            const int pb = dd + Nn + Nn + 1;               // window position of x_{k+N+1} for output 0
+#pragma unroll
+            for (int kk = ZK - 1; kk >= 0; --kk) {
+                Bc = __fma_rn(a, Bc, xc[kk]);
+                if (kk < ZK - 1) Bc = __fma_rn(naN1, lds1(pb + kk), Bc);
+                acc[kk] = __dmul_rn(cn, __dsub_rn(__dadd_rn(Fv[kk], Bc), xc[kk]));
+            }
+        } else {
         double w[2 * ZK - 1];
 #pragma unroll
         for (int i = 0; i < ZK; ++i) acc[i] = 0.0;
@@ -452,8 +585,9 @@ __global__ void __launch_bounds__(128) zsweep_epilogue_kernel(const __grid_const
 #pragma unroll
             for (int i = 0; i < ZK - 1; ++i) w[i] = w[i + ZK];
         }
+        }
         __syncwarp();                    // every lane is done with this buffer's window: it becomes the transpose scratch
-        const long long t2 = (P.debug & 16) ? clock64() : 0;
+        const long long t2 = (P.debug & (16 | 64)) ? clock64() : 0;
 
         // ---- epilogue of this (strip, field) ----
         {
@@ -585,6 +719,10 @@ __global__ void __launch_bounds__(128) zsweep_epilogue_kernel(const __grid_const
             }
             __syncwarp();                // scratch reads are done before the buffer is refilled by the next-but-one unit
         }
+        if (trace_slot >= 0 && lane == 0 && n < 63) {
+            unsigned long long* tr = P.prof + 16 + trace_slot * 256 + 4 * n;
+            tr[0] = (unsigned long long)tunit; tr[1] = (unsigned long long)t1; tr[2] = (unsigned long long)t2; tr[3] = (unsigned long long)clock64();
+        }
         if ((P.debug & 16) && lane == 0) {
             const long long t3 = clock64();
             atomicAdd(P.prof + 0, (unsigned long long)(t1 - t0));     // waiting for the staged unit
@@ -594,6 +732,13 @@ __global__ void __launch_bounds__(128) zsweep_epilogue_kernel(const __grid_const
             atomicAdd(P.prof + 4, 1ull);
         }
         if (!have_next) {
+            if (lane == 0) tl_stamp(P.tl, 1);
+            if ((P.debug & 64) && lane == 0) {
+                unsigned long long gt;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+                atomicMax(P.prof + 2304 + smid, gt);
+                atomicAdd(P.prof + 2560 + smid, (unsigned long long)(n + 1));
+            }
             if ((P.debug & 16) && lane == 0) {
                 const unsigned long long life = (unsigned long long)(clock64() - tstart);
                 atomicAdd(P.prof + 5, life);
@@ -655,8 +800,14 @@ cudaError_t launch_noise(const NoiseParams& P, const PlaneDev& D, cudaStream_t s
     if (P.n_arrays == 0) return cudaSuccess;
     int max_seg = 0;
     for (int a = 0; a < P.n_arrays; ++a) max_seg = P.a[a].n_seg > max_seg ? P.a[a].n_seg : max_seg;
+    if (P.resident_ctas > 0) {
+        NoiseParams Q = P;
+        Q.max_seg = max_seg;
+        noise_kernel<<<(unsigned)P.resident_ctas, NOISE_THREADS, 0, st>>>(Q, D);
+        return cudaGetLastError();
+    }
     dim3 grid((unsigned)P.chunks, (unsigned)max_seg, (unsigned)P.n_arrays);
-    noise_kernel<<<grid, 128, 0, st>>>(P, D);
+    noise_kernel<<<grid, NOISE_THREADS, 0, st>>>(P, D);
     return cudaGetLastError();
 }
 
@@ -677,6 +828,7 @@ cudaError_t launch_zsweep_simple(const PlaneDev& D, const StepConsts& S, cudaStr
 constexpr int Y_RC = 8, Y_NS = 6;
 
 size_t ysweep_smem_bytes() { return sizeof(YSmem<Y_RC, Y_NS>); }
+int noise_threads() { return NOISE_THREADS; }
 int ysweep_rc() { return Y_RC; }
 
 cudaError_t ysweep_prepare() {

@@ -8,6 +8,7 @@ cudaError_t launch_noise(const NoiseParams& P, const PlaneDev& D, cudaStream_t s
 cudaError_t launch_ysweep_simple(const PlaneDev& D, cudaStream_t st);
 cudaError_t launch_zsweep_simple(const PlaneDev& D, const StepConsts& S, cudaStream_t st);
 size_t ysweep_smem_bytes();
+int noise_threads();          // CTA size of noise_kernel (NoiseParams::chunks = ceil(max_np / noise_threads()))
 int ysweep_rc();
 cudaError_t ysweep_prepare();
 cudaError_t launch_ysweep_tma(const YMaps& maps, const YParams& P, int n_items, cudaStream_t st);
