@@ -355,8 +355,12 @@ void build_device(dfb_filter_s& H) {
             cudaDeviceProp prop;
             CUDA_TRY(cudaGetDeviceProperties(&prop, H.device));
             int zb = 1;
-            CUDA_TRY(zsweep_prepare(Z.zk, (size_t)Z.smem_bytes, &zb));
-            if (std::getenv("DFB_Z_BLOCKS_PER_SM")) zb = std::min(zb, std::atoi(std::getenv("DFB_Z_BLOCKS_PER_SM")));
+            CUDA_TRY(zsweep_prepare(Z.zk, Z.zmode, (size_t)Z.smem_bytes, &zb));
+            // The recursive form is bound by shared-memory traffic and latency, not by the fp64 pipe: two CTAs per SM run it as
+            // fast as three would in the step as a whole, because the third's registers go to the next step's noise CTAs, which
+            // then run beside the sweep instead of after it (measured: 0.168 vs 0.176 ms/step on 1024x2048 profile).
+            if (Z.zmode == 1) zb = std::min(zb, 2);
+            if (std::getenv("DFB_Z_BLOCKS_PER_SM")) zb = std::min(std::max(zb, 3), std::atoi(std::getenv("DFB_Z_BLOCKS_PER_SM")));
             Z.nblocks = std::max(1, std::min(std::max(zb, 1) * prop.multiProcessorCount, (Z.n_units + 3) / 4));
             Z.n_sm = prop.multiProcessorCount;
             {

@@ -15,6 +15,16 @@
 #include "device.cuh"
 #include "kernels.hpp"
 
+// registers per thread of the recursive z-sweep (measured: capping it below 168 to fit a third CTA plus noise CTAs spills and loses)
+#ifndef Z_REC_MAXNREG
+#define Z_REC_MAXNREG 168
+#endif
+#ifndef Z_EPI_PIECEWISE
+#define Z_EPI_PIECEWISE 0
+#endif
+#ifndef Z_FO_EARLY
+#define Z_FO_EARLY 1
+#endif
 #ifndef NOISE_THREADS
 #define NOISE_THREADS 128
 #endif
@@ -384,8 +394,8 @@ __device__ __forceinline__ void z_issue_unit(const ZParams& P, const ZMaps& maps
     tma_load_1d(reinterpret_cast<unsigned char*>(buf) + P.box_bytes, P.coef_pad + (size_t)desc[6] * 16, cbytes, bar);
 }
 
-template <int ZK>
-__global__ void __launch_bounds__(128) zsweep_epilogue_kernel(const __grid_constant__ ZMaps maps, const ZParams P) {
+template <int ZK, int MODE>
+__global__ void __maxnreg__(MODE == 1 ? Z_REC_MAXNREG : 168) zsweep_epilogue_kernel(const __grid_constant__ ZMaps maps, const ZParams P) {
     constexpr int Z_STRIP = 32 * ZK;         // columns per unit
     constexpr int LB = ZK * 8;               // bytes per staged line (= one lane's ZK samples): 128 -> SWIZZLE_128B, 64 -> SWIZZLE_64B
     constexpr int PPL = ZK / 2;              // 16-byte pieces per line
@@ -466,17 +476,20 @@ __global__ void __launch_bounds__(128) zsweep_epilogue_kernel(const __grid_const
 
         // filt_old of this strip, coalesced (piece p = lane + 32 m): requested now, consumed after the tap loop
         double2 fo_pc[ZK / 2];
-        if (blend && coalesced) {
+        auto request_fo = [&]() {
+            if (blend && coalesced) {
 #pragma unroll
-            for (int m = 0; m < ZK / 2; ++m) fo_pc[m] = __ldcs(reinterpret_cast<const double2*>(F.filt_old + sbase) + lane + 32 * m);
-        }
+                for (int m = 0; m < ZK / 2; ++m) fo_pc[m] = __ldcs(reinterpret_cast<const double2*>(F.filt_old + sbase) + lane + 32 * m);
+            }
+        };
+        if (MODE == 0 || Z_FO_EARLY) request_fo();      // direct form: the long tap loop hides the latency; the recursive form asks later (registers)
         const long long t0 = (P.debug & 16) ? clock64() : 0;
         mbar_wait(&bars[n & 1], (n >> 1) & 1);
         const long long t1 = (P.debug & (16 | 64)) ? clock64() : 0;
         unsigned char* cbuf = wbase + (size_t)(n & 1) * P.unit_bytes;
         const double* B = reinterpret_cast<const double*>(cbuf + P.box_bytes);
         double acc[ZK];
-        if (P.zmode == 1) {
+        if (MODE == 1) {
             // ---- recursive form ----
             // The reference's coefficients are a truncated two-sided exponential, b_i = a^|i| / s, a = exp(-2 pi / N)
             // (df.cpp:168-177), so with F_k = sum_{i=0..N} a^i x_{k-i} and B_k = sum_{i=0..N} a^i x_{k+i}
@@ -541,6 +554,7 @@ __global__ void __launch_bounds__(128) zsweep_epilogue_kernel(const __grid_const
                 Fc = __fma_rn(aZK, Fc, xa[0]);
                 Bc = __fma_rn(aZK, Bc, xb[0]);
             }
+            if (!Z_FO_EARLY) request_fo();                 // the line buffers above are dead: their registers carry filt_old
             double xc[ZK], Fv[ZK];
             load_line(cl, xc);
 #pragma unroll
@@ -604,6 +618,54 @@ __global__ void __launch_bounds__(128) zsweep_epilogue_kernel(const __grid_const
                 __syncwarp();
                 __threadfence();
             }
+#if Z_EPI_PIECEWISE
+            if (coalesced) {
+                // Lane l owns line l (its ZK cells) of a 32-line scratch tile; global memory wants piece p = lane + 32 m.  Both
+                // views are conflict-free under the same XOR swizzle.  ONE transpose (the filtered values), then the whole
+                // epilogue is elementwise on pieces: filt_old and u's field arrive, and all outputs leave, in piece order.
+                const int own = lane * LB, osw = swz(lane) << 4;
+#pragma unroll
+                for (int i = 0; i < ZK / 2; ++i)
+                    *reinterpret_cast<double2*>(cbuf + own + ((i << 4) ^ osw)) = make_double2(acc[2 * i], acc[2 * i + 1]);
+                __syncwarp();
+                double2 zp[ZK / 2];
+#pragma unroll
+                for (int m = 0; m < ZK / 2; ++m) {
+                    const int pc_ = lane + 32 * m, r = pc_ / PPL;
+                    zp[m] = *reinterpret_cast<const double2*>(cbuf + r * LB + ((((pc_ % PPL) ^ swz(r))) << 4));
+                }
+                double2 ufp[ZK / 2];
+                double rc1 = 0.0;
+                if (f == 1) {
+                    rc1 = __ldg(rcp + 1);
+#pragma unroll
+                    for (int m = 0; m < ZK / 2; ++m) ufp[m] = __ldcg(reinterpret_cast<const double2*>(D.f[0].filt_old + sbase) + lane + 32 * m);
+                }
+                const bool sra = f == 0 && blend;                                                   // get_rho_T_fluc, df.cpp:474-481
+                double rc4 = 0.0, rc5 = 0.0, rc6 = 0.0;
+                if (sra) { rc4 = __ldg(rcp + 4); rc5 = __ldg(rcp + 5); rc6 = __ldg(rcp + 6); }
+                double2* g_fold = reinterpret_cast<double2*>(F.filt_old + sbase) + lane;
+                double2* g_fluc = reinterpret_cast<double2*>(F.fluc + sbase) + lane;
+                double2* g_T = reinterpret_cast<double2*>(D.T_fluc + sbase) + lane;
+                double2* g_rho = reinterpret_cast<double2*>(D.rho_fluc + sbase) + lane;
+#pragma unroll
+                for (int m = 0; m < ZK / 2; ++m) {
+                    double2 z = zp[m];
+                    if (blend) {                                                                     // correlate_fields, df.cpp:415
+                        z.x = epi_blend(fo_pc[m].x, sa, z.x, sb);
+                        z.y = epi_blend(fo_pc[m].y, sa, z.y, sb);
+                    }
+                    g_fold[32 * m] = z;                                                              // filt_old <- filt, df.cpp:440-442
+                    double2 o = make_double2(epi_scale(rc_own, z.x), epi_scale(rc_own, z.y));       // df.cpp:436,438; v.filt term of 437
+                    if (f == 1) { o.x = epi_cross(rc1, ufp[m].x, o.x); o.y = epi_cross(rc1, ufp[m].y, o.y); }   // df.cpp:437
+                    __stcs(g_fluc + 32 * m, o);
+                    if (sra) {
+                        const double tx = __dmul_rn(rc4, o.x), ty = __dmul_rn(rc4, o.y);
+                        __stcs(g_T + 32 * m, make_double2(__dmul_rn(tx, rc5), __dmul_rn(ty, rc5)));
+                        __stcs(g_rho + 32 * m, make_double2(__dmul_rn(-tx, rc6), __dmul_rn(-ty, rc6)));
+                    }
+                }
+#else
             if (coalesced) {
                 // Lane l owns line l (its ZK cells) of a 32-line scratch tile; global memory wants piece
                 // p = lane + 32 m.  Both views are conflict-free under the same XOR swizzle.
@@ -690,6 +752,7 @@ __global__ void __launch_bounds__(128) zsweep_epilogue_kernel(const __grid_const
                     for (int i = 0; i < ZK; ++i) t[i] = __dmul_rn(-z[i], rc6);
                     store_strip(D.rho_fluc + sbase, t, true);
                 }
+#endif
             } else if (active) {
                 double* __restrict__ fold = F.filt_old + base;
                 double* __restrict__ fluc = F.fluc + base;
@@ -854,22 +917,25 @@ cudaError_t launch_ysweep_tma(const YMaps& maps, const YParams& P, int n_tiles, 
     return cudaLaunchKernelEx(&cfg, ysweep_tma_kernel<Y_RC, Y_NS>, maps, P);
 }
 
-static const void* zsweep_fn(int zk) { return zk == 16 ? (const void*)zsweep_epilogue_kernel<16> : (const void*)zsweep_epilogue_kernel<8>; }
+static const void* zsweep_fn(int zk, int mode) {
+    if (zk == 16) return mode == 1 ? (const void*)zsweep_epilogue_kernel<16, 1> : (const void*)zsweep_epilogue_kernel<16, 0>;
+    return mode == 1 ? (const void*)zsweep_epilogue_kernel<8, 1> : (const void*)zsweep_epilogue_kernel<8, 0>;
+}
 
-cudaError_t zsweep_prepare(int zk, size_t smem, int* blocks_per_sm) {
-    cudaError_t e = cudaFuncSetAttribute(zsweep_fn(zk), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+cudaError_t zsweep_prepare(int zk, int mode, size_t smem, int* blocks_per_sm) {
+    const void* fn = zsweep_fn(zk, mode);
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(zsweep_fn(zk), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
-    if (zk == 16) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, zsweep_epilogue_kernel<16>, 128, smem);
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, zsweep_epilogue_kernel<8>, 128, smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, fn, 128, smem);
 }
 
 cudaError_t launch_zsweep_tuned(const ZMaps& maps, const ZParams& P, cudaStream_t st) {
     cudaLaunchAttribute attr;
     cudaLaunchConfig_t cfg = pdl_config((unsigned)P.nblocks, 128, (size_t)P.smem_bytes, st, &attr);
-    if (P.zk == 16) return cudaLaunchKernelEx(&cfg, zsweep_epilogue_kernel<16>, maps, P);
-    return cudaLaunchKernelEx(&cfg, zsweep_epilogue_kernel<8>, maps, P);
+    void* args[2] = {const_cast<ZMaps*>(&maps), const_cast<ZParams*>(&P)};
+    return cudaLaunchKernelExC(&cfg, zsweep_fn(P.zk, P.zmode), args);
 }
 
 cudaError_t launch_dfma_peak(double* out, int blocks, int iters, cudaStream_t st) {

@@ -12,7 +12,7 @@ int noise_threads();          // CTA size of noise_kernel (NoiseParams::chunks =
 int ysweep_rc();
 cudaError_t ysweep_prepare();
 cudaError_t launch_ysweep_tma(const YMaps& maps, const YParams& P, int n_items, cudaStream_t st);
-cudaError_t zsweep_prepare(int zk, size_t smem, int* blocks_per_sm);
+cudaError_t zsweep_prepare(int zk, int mode, size_t smem, int* blocks_per_sm);
 cudaError_t launch_zsweep_tuned(const ZMaps& maps, const ZParams& P, cudaStream_t st);
 cudaError_t launch_stats(const PlaneDev& D, double* sums, cudaStream_t st);
 cudaError_t launch_dfma_peak(double* out, int blocks, int iters, cudaStream_t st);
