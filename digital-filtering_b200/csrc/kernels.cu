@@ -517,57 +517,102 @@ __global__ void __maxnreg__(MODE == 1 ? Z_REC_MAXNREG : 168) zsweep_epilogue_ker
                 const int line = lane + p / ZK, e = p % ZK;
                 return *reinterpret_cast<const double*>(cbuf + line * LB + ((((e >> 1) ^ swz(line))) << 4) + (e & 1) * 8);
             };
-            // Horner over whole lines as a binary tree: the line's ZK terms are folded pairwise with a, a^2, a^4, (a^8) -- independent
-            // of the running value -- and only one FMA per line, F <- a^ZK F + T, is on the dependent chain.
+            // Horner over whole lines as a binary tree: a line's ZK terms are folded pairwise with a, a^2, a^4, (a^8), independent of
+            // the running value; only one FMA per line, F <- a^ZK F + T, is on the dependent chain.  A line's sums do not depend
+            // on which lane wants them (lanes l and l+1 share all but one line of their windows), so every line of the staged
+            // window is read and folded ONCE -- lane l folds line l and, if the window has it, line l + 32 -- and the lanes pick the
+            // sums they need with shuffles: 3-4 line reads per lane instead of 2 cl + 1.
             const double a2 = hdr[5], a4 = hdr[6], a8 = hdr[7], aZK = ZK == 16 ? hdr[8] : hdr[7];
-            double Fc = 0.0, Bc = 0.0;
-            for (int m = 0; m < cl; ++m) {
-                double xa[ZK], xb[ZK];
-                load_line(m, xa);                          // causal: oldest line first, element 0 oldest
-                load_line(2 * cl - m, xb);                 // anti-causal: farthest line first, element ZK-1 farthest
-                if (m == 0) {
+            auto fold_c = [&](const double* x, int first) {        // sum_e a^(ZK-1-e) x_e over e >= first (element 0 is the oldest)
+                double t[ZK / 2];
 #pragma unroll
-                    for (int e = 0; e < ZK; ++e) {         // outside the window: contributes nothing
-                        if (e < dd) xa[e] = 0.0;
-                        if (e > ef) xb[e] = 0.0;
-                    }
-                }
+                for (int q = 0; q < ZK / 2; ++q) t[q] = __fma_rn(a, (2 * q < first) ? 0.0 : x[2 * q], (2 * q + 1 < first) ? 0.0 : x[2 * q + 1]);
 #pragma unroll
-                for (int i = 0; i < ZK / 2; ++i) {
-                    xa[i] = __fma_rn(a, xa[2 * i], xa[2 * i + 1]);                     // newer element has the smaller power
-                    xb[i] = __fma_rn(a, xb[2 * i + 1], xb[2 * i]);
-                }
+                for (int q = 0; q < ZK / 4; ++q) t[q] = __fma_rn(a2, t[2 * q], t[2 * q + 1]);
 #pragma unroll
-                for (int i = 0; i < ZK / 4; ++i) {
-                    xa[i] = __fma_rn(a2, xa[2 * i], xa[2 * i + 1]);
-                    xb[i] = __fma_rn(a2, xb[2 * i + 1], xb[2 * i]);
-                }
+                for (int q = 0; q < ZK / 8; ++q) t[q] = __fma_rn(a4, t[2 * q], t[2 * q + 1]);
+                if (ZK == 16) t[0] = __fma_rn(a8, t[0], t[1]);
+                return t[0];
+            };
+            auto fold_a = [&](const double* x, int last) {         // sum_e a^e x_e over e <= last (element 0 is the nearest)
+                double t[ZK / 2];
 #pragma unroll
-                for (int i = 0; i < ZK / 8; ++i) {
-                    xa[i] = __fma_rn(a4, xa[2 * i], xa[2 * i + 1]);
-                    xb[i] = __fma_rn(a4, xb[2 * i + 1], xb[2 * i]);
+                for (int q = 0; q < ZK / 2; ++q) t[q] = __fma_rn(a, (2 * q + 1 > last) ? 0.0 : x[2 * q + 1], (2 * q > last) ? 0.0 : x[2 * q]);
+#pragma unroll
+                for (int q = 0; q < ZK / 4; ++q) t[q] = __fma_rn(a2, t[2 * q + 1], t[2 * q]);
+#pragma unroll
+                for (int q = 0; q < ZK / 8; ++q) t[q] = __fma_rn(a4, t[2 * q + 1], t[2 * q]);
+                if (ZK == 16) t[0] = __fma_rn(a8, t[1], t[0]);
+                return t[0];
+            };
+            double Fc, Bc;
+            if (2 * cl <= 32) {
+            double TcA, TcM, TaA, TaMA, TcB = 0.0, TaB = 0.0, TaMB = 0.0;
+            {
+                double x[ZK];
+                load_line(0, x);                                   // line `lane`
+                TcA = fold_c(x, 0);
+                TcM = dd ? fold_c(x, dd) : TcA;                    // as the first line of this lane's own window: elements before d are outside
+                TaA = fold_a(x, ZK - 1);
+                TaMA = ef < ZK - 1 ? fold_a(x, ef) : TaA;          // as the farthest line of lane (lane - 2 cl)'s window: elements after ef are outside
+                if (lane < 2 * cl) {                               // line `lane + 32` exists
+                    load_line(32, x);
+                    TcB = fold_c(x, 0);
+                    TaB = fold_a(x, ZK - 1);
+                    TaMB = ef < ZK - 1 ? fold_a(x, ef) : TaB;
                 }
-                if (ZK == 16) {
-                    xa[0] = __fma_rn(a8, xa[0], xa[1]);
-                    xb[0] = __fma_rn(a8, xb[1], xb[0]);
+            }
+            auto pick = [&](double vA, double vB, int line) {      // the sum of window line `line` of this unit (all lanes call together)
+                const double fa = __shfl_sync(0xffffffffu, vA, line & 31), fb = __shfl_sync(0xffffffffu, vB, line & 31);
+                return line < 32 ? fa : fb;
+            };
+            Fc = TcM;
+            for (int m = 1; m < cl; ++m) Fc = __fma_rn(aZK, Fc, pick(TcA, TcB, lane + m));
+            Bc = pick(TaMA, TaMB, lane + 2 * cl);
+            for (int m = 1; m < cl; ++m) Bc = __fma_rn(aZK, Bc, pick(TaA, TaB, lane + 2 * cl - m));
+            } else {
+                // windows longer than 64 lines (N > 256 at ZK = 16): every lane folds its own lines, same sums in the same order
+                Fc = 0.0; Bc = 0.0;
+                for (int m = 0; m < cl; ++m) {
+                    double x[ZK];
+                    load_line(m, x);
+                    Fc = __fma_rn(aZK, Fc, fold_c(x, m == 0 ? dd : 0));
+                    load_line(2 * cl - m, x);
+                    Bc = __fma_rn(aZK, Bc, fold_a(x, m == 0 ? ef : ZK - 1));
                 }
-                Fc = __fma_rn(aZK, Fc, xa[0]);
-                Bc = __fma_rn(aZK, Bc, xb[0]);
             }
             if (!Z_FO_EARLY) request_fo();                 // the line buffers above are dead: their registers carry filt_old
             double xc[ZK], Fv[ZK];
             load_line(cl, xc);
+            // the samples each step drops: x_{k-N-1} = window positions d .. d+ZK-2, x_{k+N+1} = positions d+2N+1 .. d+2N+ZK-1.
+            // For even d (even N) they are 16-byte aligned runs: ZK/2 vector loads each; otherwise scalar loads.
+            const int pb = dd + Nn + Nn + 1;               // window position of x_{k+N+1} for output 0
+            double xo[ZK], xq[ZK];
+            if ((dd & 1) == 0) {
+                auto load_run = [&](int p0, double* x) {   // ZK samples from even window position p0
+#pragma unroll
+                    for (int q = 0; q < ZK / 2; ++q) {
+                        const int pc_ = (p0 >> 1) + q, line = lane + pc_ / PPL;
+                        const double2 t = *reinterpret_cast<const double2*>(cbuf + line * LB + ((((pc_ % PPL) ^ swz(line))) << 4));
+                        x[2 * q] = t.x; x[2 * q + 1] = t.y;
+                    }
+                };
+                load_run(dd, xo);                          // xo[kk-1] = x_{k-N-1} of output kk
+                load_run(pb - 1, xq);                      // xq[kk+1] = x_{k+N+1} of output kk
+            } else {
+#pragma unroll
+                for (int kk = 0; kk < ZK - 1; ++kk) { xo[kk] = lds1(dd + kk); xq[kk + 1] = lds1(pb + kk); }
+            }
 #pragma unroll
             for (int kk = 0; kk < ZK; ++kk) {
                 Fc = __fma_rn(a, Fc, xc[kk]);
-                if (kk > 0) Fc = __fma_rn(naN1, lds1(dd + kk - 1), Fc);
+                if (kk > 0) Fc = __fma_rn(naN1, xo[kk - 1], Fc);
                 Fv[kk] = Fc;
             }
-            const int pb = dd + Nn + Nn + 1;               // window position of x_{k+N+1} for output 0
 #pragma unroll
             for (int kk = ZK - 1; kk >= 0; --kk) {
                 Bc = __fma_rn(a, Bc, xc[kk]);
-                if (kk < ZK - 1) Bc = __fma_rn(naN1, lds1(pb + kk), Bc);
+                if (kk < ZK - 1) Bc = __fma_rn(naN1, xq[kk + 1], Bc);
                 acc[kk] = __dmul_rn(cn, __dsub_rn(__dadd_rn(Fv[kk], Bc), xc[kk]));
             }
         } else {
