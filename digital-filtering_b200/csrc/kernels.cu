@@ -19,6 +19,17 @@
 #ifndef Z_REC_MAXNREG
 #define Z_REC_MAXNREG 168
 #endif
+// measured on the same box (1024x2048 profile, ms/step): baseline 0.1674; descriptor requested before the epilogue 0.1613;
+// deferred u->v publication 0.1617 alone but 0.1679 combined (register allocation); early fetch of u's field for v strips 0.1695
+#ifndef Z_DEFER_PUBLISH
+#define Z_DEFER_PUBLISH 0
+#endif
+#ifndef Z_DESC_EARLY
+#define Z_DESC_EARLY 1
+#endif
+#ifndef Z_UF_EARLY
+#define Z_UF_EARLY 0
+#endif
 #ifndef Z_EPI_PIECEWISE
 #define Z_EPI_PIECEWISE 0
 #endif
@@ -394,6 +405,12 @@ __device__ __forceinline__ void z_issue_unit(const ZParams& P, const ZMaps& maps
     tma_load_1d(reinterpret_cast<unsigned char*>(buf) + P.box_bytes, P.coef_pad + (size_t)desc[6] * 16, cbytes, bar);
 }
 
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
 template <int ZK, int MODE>
 __global__ void __maxnreg__(MODE == 1 ? Z_REC_MAXNREG : 168) zsweep_epilogue_kernel(const __grid_constant__ ZMaps maps, const ZParams P) {
     constexpr int Z_STRIP = 32 * ZK;         // columns per unit
@@ -451,6 +468,7 @@ __global__ void __maxnreg__(MODE == 1 ? Z_REC_MAXNREG : 168) zsweep_epilogue_ker
     //   top:    stage unit n+1 (its descriptor is already in shared memory), claim unit n+2 (atomic, result not awaited)
     //   middle: tap loop of unit n
     //   bottom: epilogue of unit n; fetch the descriptor of unit n+2 into the slot unit n just vacated
+    int pend_flag = -1;     // u strip whose completion flag is not published yet (published after the NEXT unit's taps: the fence is then free)
     for (int n = 0;; ++n) {
         const int* dcur = descs + (n & 1) * 8;
         int* dnext = descs + ((n + 1) & 1) * 8;
@@ -482,7 +500,20 @@ __global__ void __maxnreg__(MODE == 1 ? Z_REC_MAXNREG : 168) zsweep_epilogue_ker
                 for (int m = 0; m < ZK / 2; ++m) fo_pc[m] = __ldcs(reinterpret_cast<const double2*>(F.filt_old + sbase) + lane + 32 * m);
             }
         };
-        if (MODE == 0 || Z_FO_EARLY) request_fo();      // direct form: the long tap loop hides the latency; the recursive form asks later (registers)
+        if (MODE == 0 || Z_FO_EARLY) request_fo();
+        // v' = b u_filt + c v_filt (df.cpp:437) needs u's blended field of this strip, written by the u unit (queued far ahead
+        // of every v unit).  If its stamp is already there -- practically always -- fetch the field now, behind the taps.
+        double2 uf_pc[ZK / 2];
+        bool uf_early = false;
+        if (Z_UF_EARLY && f == 1 && coalesced) {
+            int fv = 0;
+            if (lane == 0) fv = ld_acquire_gpu(P.flags + flag_idx);
+            uf_early = __shfl_sync(0xffffffffu, fv, 0) == P.stamp;
+            if (uf_early) {
+#pragma unroll
+                for (int m = 0; m < ZK / 2; ++m) uf_pc[m] = __ldcg(reinterpret_cast<const double2*>(D.f[0].filt_old + sbase) + lane + 32 * m);
+            }
+        }      // direct form: the long tap loop hides the latency; the recursive form asks later (registers)
         const long long t0 = (P.debug & 16) ? clock64() : 0;
         mbar_wait(&bars[n & 1], (n >> 1) & 1);
         const long long t1 = (P.debug & (16 | 64)) ? clock64() : 0;
@@ -646,6 +677,18 @@ __global__ void __maxnreg__(MODE == 1 ? Z_REC_MAXNREG : 168) zsweep_epilogue_ker
         }
         }
         __syncwarp();                    // every lane is done with this buffer's window: it becomes the transpose scratch
+        if (pend_flag >= 0) {            // the previous unit was a u strip: its stores were issued a whole tap phase ago
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) *reinterpret_cast<volatile int*>(P.flags + pend_flag) = P.stamp;
+            pend_flag = -1;
+        }
+        // descriptor of unit n+2 (claimed at the top of this unit): request it now, store it after the epilogue
+        int nn = P.n_units, dreg = 0;
+        if (Z_DESC_EARLY && have_next) {
+            nn = __shfl_sync(0xffffffffu, claim, 0);
+            if (nn < P.n_units && lane < 8) dreg = __ldg(reinterpret_cast<const int*>(P.units + nn) + lane);
+        }
         const long long t2 = (P.debug & (16 | 64)) ? clock64() : 0;
 
         // ---- epilogue of this (strip, field) ----
@@ -656,12 +699,12 @@ __global__ void __maxnreg__(MODE == 1 ? Z_REC_MAXNREG : 168) zsweep_epilogue_ker
             if (f == 1) {
                 // v' = b u_filt + c v_filt (df.cpp:437): u's blended field of this strip comes from the u unit
                 // (queued far ahead of every v unit); wait for its stamp, then read it like any other global data
-                if (lane == 0) {
-                    const volatile int* fl = P.flags + flag_idx;
-                    while (*fl != P.stamp) __nanosleep(100);
+                if (!uf_early) {
+                    if (lane == 0) {
+                        while (ld_acquire_gpu(P.flags + flag_idx) != P.stamp) __nanosleep(100);
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
-                __threadfence();
             }
 #if Z_EPI_PIECEWISE
             if (coalesced) {
@@ -684,7 +727,8 @@ __global__ void __maxnreg__(MODE == 1 ? Z_REC_MAXNREG : 168) zsweep_epilogue_ker
                 if (f == 1) {
                     rc1 = __ldg(rcp + 1);
 #pragma unroll
-                    for (int m = 0; m < ZK / 2; ++m) ufp[m] = __ldcg(reinterpret_cast<const double2*>(D.f[0].filt_old + sbase) + lane + 32 * m);
+                    for (int m = 0; m < ZK / 2; ++m)
+                        ufp[m] = uf_early ? uf_pc[m] : __ldcg(reinterpret_cast<const double2*>(D.f[0].filt_old + sbase) + lane + 32 * m);
                 }
                 const bool sra = f == 0 && blend;                                                   // get_rho_T_fluc, df.cpp:474-481
                 double rc4 = 0.0, rc5 = 0.0, rc6 = 0.0;
@@ -782,7 +826,8 @@ __global__ void __maxnreg__(MODE == 1 ? Z_REC_MAXNREG : 168) zsweep_epilogue_ker
                 if (f == 1) {
                     const double rc1 = __ldg(rcp + 1);
                     double uf[ZK];
-                    load_strip(D.f[0].filt_old + sbase, uf);
+                    if (uf_early) { put_pieces(uf_pc); __syncwarp(); get_own(uf); __syncwarp(); }
+                    else load_strip(D.f[0].filt_old + sbase, uf);
 #pragma unroll
                     for (int i = 0; i < ZK; ++i) o[i] = epi_cross(rc1, uf[i], o[i]);            // df.cpp:437
                 }
@@ -820,10 +865,13 @@ __global__ void __maxnreg__(MODE == 1 ? Z_REC_MAXNREG : 168) zsweep_epilogue_ker
                     }
                 }
             }
-            if (f == 0) {                 // publish: this strip's blended u field is in global memory
-                __threadfence();
-                __syncwarp();
-                if (lane == 0) *reinterpret_cast<volatile int*>(P.flags + flag_idx) = P.stamp;
+            if (f == 0) {
+                if (Z_DEFER_PUBLISH) pend_flag = flag_idx;    // this strip's blended u field is on its way to global memory: publish later
+                else {
+                    __threadfence();
+                    __syncwarp();
+                    if (lane == 0) *reinterpret_cast<volatile int*>(P.flags + flag_idx) = P.stamp;
+                }
             }
             __syncwarp();                // scratch reads are done before the buffer is refilled by the next-but-one unit
         }
@@ -840,6 +888,11 @@ __global__ void __maxnreg__(MODE == 1 ? Z_REC_MAXNREG : 168) zsweep_epilogue_ker
             atomicAdd(P.prof + 4, 1ull);
         }
         if (!have_next) {
+            if (pend_flag >= 0) {
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) *reinterpret_cast<volatile int*>(P.flags + pend_flag) = P.stamp;
+            }
             if (lane == 0) tl_stamp(P.tl, 1);
             if ((P.debug & 64) && lane == 0) {
                 unsigned long long gt;
@@ -855,10 +908,13 @@ __global__ void __maxnreg__(MODE == 1 ? Z_REC_MAXNREG : 168) zsweep_epilogue_ker
             }
             break;
         }
-        // descriptor of unit n+2 into the slot unit n just vacated (the atomic was issued at the top of this unit)
-        const int nn = __shfl_sync(0xffffffffu, claim, 0);
+        // descriptor of unit n+2 into the slot unit n just vacated
         int* dfree = descs + (n & 1) * 8;
-        if (nn < P.n_units && lane < 8) dfree[lane] = __ldg(reinterpret_cast<const int*>(P.units + nn) + lane);
+        if (!Z_DESC_EARLY) {
+            nn = __shfl_sync(0xffffffffu, claim, 0);
+            if (nn < P.n_units && lane < 8) dreg = __ldg(reinterpret_cast<const int*>(P.units + nn) + lane);
+        }
+        if (nn < P.n_units && lane < 8) dfree[lane] = dreg;
         __syncwarp();
         nxt = nn;
     }

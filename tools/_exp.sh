@@ -1,5 +1,1 @@
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python tools/stepbench.py
-DFB_Z_BLOCKS_PER_SM=3 python tools/stepbench.py
-DFB_DEBUG_Z=16 python tools/zprof.py 1024x2048_profile_N128
-python tools/timeline.py | tail -2
+for v in e010_168 e110_184 e111_184 e110_200 e111_200 e010_184 e010_168; do DFB_LIB=$PWD/digital-filtering_b200/lib/$v.so python tools/stepbench.py; done
