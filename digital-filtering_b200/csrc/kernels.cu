@@ -10,6 +10,7 @@
 //                           the general (non row-uniform) path and the on-device cross-check of the tuned path
 //   dfma_peak_kernel        fp64 roofline denominator
 #include <cstdint>
+#include <cstdlib>
 #include <cstdio>
 #include "noise.cuh"
 #include "device.cuh"
@@ -57,16 +58,19 @@ __device__ __forceinline__ void noise_block(const NoiseParams& P, const PlaneDev
     const NoiseArray& A = P.a[bz];
     const int slot = bx * NOISE_THREADS + threadIdx.x;
     if (seg >= A.n_seg) return;
+    // all four table reads are requested together (the slot is clamped so that the read is always legal): one memory round trip
+    // per thread instead of two dependent ones
     const int np = A.seg_np[seg];
-    if (slot >= np) return;
     const Jump sj = reinterpret_cast<const Jump*>(A.seg_jump)[seg];
-    const Jump tj = P.slot_jump[slot];
+    const Jump tj = P.slot_jump[min(slot, P.max_np - 1)];
+    const long long q0 = A.seg_q0[seg];
+    if (slot >= np) return;
     uint64_t s = sj.A * A.state + A.inc * sj.C;
     s = tj.A * s + A.inc * tj.C;
     double z0, z1;
     normal_pair(s, A.inc, z0, z1);
 
-    const long long q = A.seg_q0[seg] + slot;
+    const long long q = q0 + slot;
     const FieldDev& F = D.f[A.field];
     if (A.kind == 0) {
         // r_ys: element e = r*NzG + g, segment = padded row r, g in [xk0, xk0+We)
@@ -995,9 +999,14 @@ size_t ysweep_smem_bytes() { return sizeof(YSmem<Y_RC, Y_NS>); }
 int noise_threads() { return NOISE_THREADS; }
 int ysweep_rc() { return Y_RC; }
 
+static size_t y_pad_smem() {      // experiment (DFB_Y_PAD_SMEM bytes): fewer resident y-sweep CTAs per SM
+    static const size_t pad = std::getenv("DFB_Y_PAD_SMEM") ? (size_t)std::atoi(std::getenv("DFB_Y_PAD_SMEM")) : 0;
+    return pad;
+}
+
 cudaError_t ysweep_prepare() {
     cudaError_t e = cudaFuncSetAttribute(ysweep_tma_kernel<Y_RC, Y_NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)sizeof(YSmem<Y_RC, Y_NS>));
+                                         (int)(sizeof(YSmem<Y_RC, Y_NS>) + y_pad_smem()));
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(ysweep_tma_kernel<Y_RC, Y_NS>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                 cudaSharedmemCarveoutMaxShared);
@@ -1014,7 +1023,7 @@ static cudaLaunchConfig_t pdl_config(unsigned grid, unsigned block, size_t smem,
 
 cudaError_t launch_ysweep_tma(const YMaps& maps, const YParams& P, int n_tiles, cudaStream_t st) {
     cudaLaunchAttribute attr;
-    cudaLaunchConfig_t cfg = pdl_config((unsigned)n_tiles, 160, sizeof(YSmem<Y_RC, Y_NS>), st, &attr);
+    cudaLaunchConfig_t cfg = pdl_config((unsigned)n_tiles, 160, sizeof(YSmem<Y_RC, Y_NS>) + y_pad_smem(), st, &attr);
     return cudaLaunchKernelEx(&cfg, ysweep_tma_kernel<Y_RC, Y_NS>, maps, P);
 }
 

@@ -1,1 +1,4 @@
-for v in e010_168 e110_184 e111_184 e110_200 e111_200 e010_184 e010_168; do DFB_LIB=$PWD/digital-filtering_b200/lib/$v.so python tools/stepbench.py; done
+DFB_LIB=$PWD/digital-filtering_b200/lib/prev.so python tools/stepbench.py
+python tools/stepbench.py
+python tools/quick_gpu.py 1024x2048_profile_N128 2>&1 | grep "variant 0" | cut -c1-330
+DFB_LIB=$PWD/digital-filtering_b200/lib/prev.so python tools/quick_gpu.py 1024x2048_profile_N128 2>&1 | grep "variant 0" | cut -c1-330
