@@ -1,4 +1,2 @@
-DFB_LIB=$PWD/digital-filtering_b200/lib/prev.so python tools/stepbench.py
-python tools/stepbench.py
-python tools/quick_gpu.py 1024x2048_profile_N128 2>&1 | grep "variant 0" | cut -c1-330
-DFB_LIB=$PWD/digital-filtering_b200/lib/prev.so python tools/quick_gpu.py 1024x2048_profile_N128 2>&1 | grep "variant 0" | cut -c1-330
+for v in n4_1_128 n8_1_128 n16_1_64 n8_1_64 n4_1_256 n8_2_128 n16_1_128 n4_1_128; do DFB_LIB=$PWD/digital-filtering_b200/lib/$v.so python tools/stepbench.py; done
+DFB_LIB=$PWD/digital-filtering_b200/lib/n8_1_128.so python tools/timeline.py | tail -2
