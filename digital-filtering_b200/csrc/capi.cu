@@ -641,6 +641,7 @@ int dfb_info(dfb_handle h, int what, int field, int64_t* out64) {
         case 4: *out64 = h->plan.taps_per_step; break;
         case 5: *out64 = h->plan.NzG; break;
         case 6: *out64 = h->device; break;
+        case 7: *out64 = h->tuned ? h->zp[0].zmode : 0; break;
         default: return fail(DFB_ERR_ARG, "unknown info selector");
     }
     return DFB_OK;
