@@ -363,15 +363,6 @@ void build_device(dfb_filter_s& H) {
             if (std::getenv("DFB_Z_BLOCKS_PER_SM")) zb = std::min(std::max(zb, 3), std::atoi(std::getenv("DFB_Z_BLOCKS_PER_SM")));
             Z.nblocks = std::max(1, std::min(std::max(zb, 1) * prop.multiProcessorCount, (Z.n_units + 3) / 4));
             Z.n_sm = prop.multiProcessorCount;
-            {
-                // one unit's tap loop when the fp64 pipe is shared by all co-resident warps of an SMSP; slots start 1/zb of that apart
-                double taps = 0;
-                for (const ZUnit& u : units) taps += (double)u.nchunk * ZKc * ZKc;
-                const double unit_cycles = 2.0 * taps / std::max<size_t>(units.size(), 1) * std::max(zb, 1);
-                const char* se = std::getenv("DFB_Z_STAGGER");
-                Z.stagger_cycles = se ? std::atoi(se) : 0;   // measured: no effect (co-resident warps spread out by themselves)
-                (void)unit_cycles;
-            }
             H.yp[0].zcounter = Z.counter;
             H.yp[1].zcounter = Z.counter + 1;
             for (int b = 0; b < 2; ++b)
@@ -464,10 +455,6 @@ void launch_noise_for(dfb_filter_s& H, int64_t step, int b, cudaStream_t st) {
     H.ybuf_step[b] = -1;                 // new noise invalidates whatever y-sweep result the set held
     fill_noise_params(H, step);
     H.np.tl = H.tl ? H.tl + (step % 64) * 8 : nullptr;
-    {   // resident shape only for the look-ahead launch on the side stream (experiment: DFB_NOISE_CTAS)
-        const char* nc = std::getenv("DFB_NOISE_CTAS");
-        H.np.resident_ctas = (nc && st == H.side) ? std::atoi(nc) : 0;
-    }
     CUDA_TRY(launch_noise(H.np, H.D[b], st));
     CUDA_TRY(cudaEventRecord(H.ev_noise[b], st));
     H.buf_step[b] = step;
@@ -596,8 +583,7 @@ int dfb_create(const dfb_config* cfg, dfb_handle* out) {
         int prio_lo = 0, prio_hi = 0;
         CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
         CUDA_TRY(cudaStreamCreateWithPriority(&H->stream, cudaStreamNonBlocking, prio_hi));
-        const char* sp = std::getenv("DFB_SIDE_PRIO");          // experiment: 0 = lowest (default), 1 = same as the main stream
-        CUDA_TRY(cudaStreamCreateWithPriority(&H->side, cudaStreamNonBlocking, (sp && std::atoi(sp) == 1) ? prio_hi : prio_lo));
+        CUDA_TRY(cudaStreamCreateWithPriority(&H->side, cudaStreamNonBlocking, prio_lo));
         for (auto& e2 : H->ev) CUDA_TRY(cudaEventCreate(&e2));
         for (int b = 0; b < 2; ++b) {
             CUDA_TRY(cudaEventCreateWithFlags(&H->ev_noise[b], cudaEventDisableTiming));

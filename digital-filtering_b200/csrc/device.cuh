@@ -91,8 +91,6 @@ struct NoiseParams {
     int n_arrays;
     int max_np;                 // largest segment (pairs)
     int chunks;                 // ceil(max_np / 128)
-    int max_seg;                // resident shape: segments of the longest array (set by the launcher)
-    int resident_ctas;          // > 0: resident shape with that many CTAs (see noise_kernel)
     unsigned long long* tl;     // development aid (DFB_TIMELINE): [start, end] globaltimer stamps of this launch, or nullptr
 };
 
@@ -137,7 +135,6 @@ struct ZParams {
     int n_sm;                    // CTAs are dealt round-robin to the SMs: CTA b sits in residency slot b / n_sm of its SM
     unsigned long long* tl;      // development aid (DFB_TIMELINE), see NoiseParams
     int zmode;                   // 0: direct Toeplitz tap loop; 1: recursive evaluation of the exponential window
-    int stagger_cycles;          // start-up delay per residency slot (see the kernel): keeps co-resident warps out of phase
     int debug;                   // development probes only (0 in production)
     unsigned long long* prof;    // [8] cycle counters filled when debug & 16
 };

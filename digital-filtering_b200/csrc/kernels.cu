@@ -2,7 +2,8 @@
 //
 //   noise_kernel            H1  generate_white_noise   df.cpp:332-349  (replaced: counter-based pcg32, see noise.cuh)
 //   ysweep_tma_kernel       H2y filtering_sweeps, y    df.cpp:360-383  tuned: TMA-staged slabs, dense band matrices
-//   zsweep_epilogue_kernel  H2z filtering_sweeps, z    df.cpp:386-405  tuned: Toeplitz register window
+//   zsweep_epilogue_kernel  H2z filtering_sweeps, z    df.cpp:386-405  tuned: <ZK,1> recursive evaluation of the exponential
+//                                                                      window (default), <ZK,0> direct Toeplitz register window
 //                         + H3  correlate_fields       df.cpp:408-417
 //                         + H4  apply_RST_scaling      df.cpp:419-447
 //                         + H5  get_rho_T_fluc         df.cpp:470-485  (one epilogue, every output written once)
@@ -19,23 +20,6 @@
 // registers per thread of the recursive z-sweep (measured: capping it below 168 to fit a third CTA plus noise CTAs spills and loses)
 #ifndef Z_REC_MAXNREG
 #define Z_REC_MAXNREG 168
-#endif
-// measured on the same box (1024x2048 profile, ms/step): baseline 0.1674; descriptor requested before the epilogue 0.1613;
-// deferred u->v publication 0.1617 alone but 0.1679 combined (register allocation); early fetch of u's field for v strips 0.1695
-#ifndef Z_DEFER_PUBLISH
-#define Z_DEFER_PUBLISH 0
-#endif
-#ifndef Z_DESC_EARLY
-#define Z_DESC_EARLY 1
-#endif
-#ifndef Z_UF_EARLY
-#define Z_UF_EARLY 0
-#endif
-#ifndef Z_EPI_PIECEWISE
-#define Z_EPI_PIECEWISE 0
-#endif
-#ifndef Z_FO_EARLY
-#define Z_FO_EARLY 1
 #endif
 // pairs per thread of the noise kernel, processed one after the other (measured ms/step on 1024x2048 profile: 1 -> 0.158,
 // 2 -> 0.147, 4 -> 0.143, 8 -> 0.147, 16 -> 0.152): fewer, longer-lived CTAs slot in beside the sweeps' CTAs much better
@@ -114,22 +98,8 @@ __device__ __forceinline__ void noise_block(const NoiseParams& P, const PlaneDev
     for (int r = 0; r < NOISE_PAIRS; ++r) noise_block1(P, D, (bx * NOISE_PAIRS + r) * NOISE_THREADS + threadIdx.x, seg, bz);
 }
 
-// Two launch shapes.  Classic: one CTA per (128 pairs, segment, array).  Resident (P.resident_ctas > 0): a small grid of CTAs
-// (about one per SM) that walk the same blocks with a stride: launched when the previous step retires, they sit beside the
-// sweeps' CTAs for the whole step as the oldest warps of their SM sub-partitions, so the warp scheduler never starves them.
+// one CTA per (NOISE_THREADS x NOISE_PAIRS pairs, segment, array)
 __global__ void __launch_bounds__(NOISE_THREADS) noise_kernel(const NoiseParams P, const PlaneDev D) {
-    if (P.resident_ctas > 0) {
-        if (threadIdx.x == 0) tl_stamp(P.tl, 0);
-        const int nseg = P.max_seg;
-        const long long total = (long long)P.chunks * nseg * P.n_arrays;
-        for (long long v = blockIdx.x; v < total; v += gridDim.x) {
-            const int bx = (int)(v % P.chunks);
-            const long long r = v / P.chunks;
-            noise_block(P, D, bx, (int)(r % nseg), (int)(r / nseg));
-        }
-        if (threadIdx.x == 0) tl_stamp(P.tl, 1);
-        return;
-    }
     if (threadIdx.x == 0 && (blockIdx.y & 31) == 0) tl_stamp(P.tl, 0);     // sampled: one row in 32 (same-address atomics)
     noise_block(P, D, blockIdx.x, blockIdx.y, blockIdx.z);
     if (threadIdx.x == 0 && (blockIdx.y & 31) == 0) tl_stamp(P.tl, 1);
@@ -485,7 +455,6 @@ __global__ void __maxnreg__(MODE == 1 ? Z_REC_MAXNREG : 168) zsweep_epilogue_ker
     //   top:    stage unit n+1 (its descriptor is already in shared memory), claim unit n+2 (atomic, result not awaited)
     //   middle: tap loop of unit n
     //   bottom: epilogue of unit n; fetch the descriptor of unit n+2 into the slot unit n just vacated
-    int pend_flag = -1;     // u strip whose completion flag is not published yet (published after the NEXT unit's taps: the fence is then free)
     for (int n = 0;; ++n) {
         const int* dcur = descs + (n & 1) * 8;
         int* dnext = descs + ((n + 1) & 1) * 8;
@@ -517,20 +486,7 @@ __global__ void __maxnreg__(MODE == 1 ? Z_REC_MAXNREG : 168) zsweep_epilogue_ker
                 for (int m = 0; m < ZK / 2; ++m) fo_pc[m] = __ldcs(reinterpret_cast<const double2*>(F.filt_old + sbase) + lane + 32 * m);
             }
         };
-        if (MODE == 0 || Z_FO_EARLY) request_fo();
-        // v' = b u_filt + c v_filt (df.cpp:437) needs u's blended field of this strip, written by the u unit (queued far ahead
-        // of every v unit).  If its stamp is already there -- practically always -- fetch the field now, behind the taps.
-        double2 uf_pc[ZK / 2];
-        bool uf_early = false;
-        if (Z_UF_EARLY && f == 1 && coalesced) {
-            int fv = 0;
-            if (lane == 0) fv = ld_acquire_gpu(P.flags + flag_idx);
-            uf_early = __shfl_sync(0xffffffffu, fv, 0) == P.stamp;
-            if (uf_early) {
-#pragma unroll
-                for (int m = 0; m < ZK / 2; ++m) uf_pc[m] = __ldcg(reinterpret_cast<const double2*>(D.f[0].filt_old + sbase) + lane + 32 * m);
-            }
-        }      // direct form: the long tap loop hides the latency; the recursive form asks later (registers)
+        request_fo();
         const long long t0 = (P.debug & 16) ? clock64() : 0;
         mbar_wait(&bars[n & 1], (n >> 1) & 1);
         const long long t1 = (P.debug & (16 | 64)) ? clock64() : 0;
@@ -629,7 +585,6 @@ __global__ void __maxnreg__(MODE == 1 ? Z_REC_MAXNREG : 168) zsweep_epilogue_ker
                     Bc = __fma_rn(aZK, Bc, fold_a(x, m == 0 ? ef : ZK - 1));
                 }
             }
-            if (!Z_FO_EARLY) request_fo();                 // the line buffers above are dead: their registers carry filt_old
             double xc[ZK], Fv[ZK];
             load_line(cl, xc);
             // the samples each step drops: x_{k-N-1} = window positions d .. d+ZK-2, x_{k+N+1} = positions d+2N+1 .. d+2N+ZK-1.
@@ -694,15 +649,9 @@ __global__ void __maxnreg__(MODE == 1 ? Z_REC_MAXNREG : 168) zsweep_epilogue_ker
         }
         }
         __syncwarp();                    // every lane is done with this buffer's window: it becomes the transpose scratch
-        if (pend_flag >= 0) {            // the previous unit was a u strip: its stores were issued a whole tap phase ago
-            __threadfence();
-            __syncwarp();
-            if (lane == 0) *reinterpret_cast<volatile int*>(P.flags + pend_flag) = P.stamp;
-            pend_flag = -1;
-        }
         // descriptor of unit n+2 (claimed at the top of this unit): request it now, store it after the epilogue
         int nn = P.n_units, dreg = 0;
-        if (Z_DESC_EARLY && have_next) {
+        if (have_next) {
             nn = __shfl_sync(0xffffffffu, claim, 0);
             if (nn < P.n_units && lane < 8) dreg = __ldg(reinterpret_cast<const int*>(P.units + nn) + lane);
         }
@@ -716,62 +665,11 @@ __global__ void __maxnreg__(MODE == 1 ? Z_REC_MAXNREG : 168) zsweep_epilogue_ker
             if (f == 1) {
                 // v' = b u_filt + c v_filt (df.cpp:437): u's blended field of this strip comes from the u unit
                 // (queued far ahead of every v unit); wait for its stamp, then read it like any other global data
-                if (!uf_early) {
-                    if (lane == 0) {
-                        while (ld_acquire_gpu(P.flags + flag_idx) != P.stamp) __nanosleep(100);
-                    }
-                    __syncwarp();
+                if (lane == 0) {
+                    while (ld_acquire_gpu(P.flags + flag_idx) != P.stamp) __nanosleep(100);
                 }
-            }
-#if Z_EPI_PIECEWISE
-            if (coalesced) {
-                // Lane l owns line l (its ZK cells) of a 32-line scratch tile; global memory wants piece p = lane + 32 m.  Both
-                // views are conflict-free under the same XOR swizzle.  ONE transpose (the filtered values), then the whole
-                // epilogue is elementwise on pieces: filt_old and u's field arrive, and all outputs leave, in piece order.
-                const int own = lane * LB, osw = swz(lane) << 4;
-#pragma unroll
-                for (int i = 0; i < ZK / 2; ++i)
-                    *reinterpret_cast<double2*>(cbuf + own + ((i << 4) ^ osw)) = make_double2(acc[2 * i], acc[2 * i + 1]);
                 __syncwarp();
-                double2 zp[ZK / 2];
-#pragma unroll
-                for (int m = 0; m < ZK / 2; ++m) {
-                    const int pc_ = lane + 32 * m, r = pc_ / PPL;
-                    zp[m] = *reinterpret_cast<const double2*>(cbuf + r * LB + ((((pc_ % PPL) ^ swz(r))) << 4));
-                }
-                double2 ufp[ZK / 2];
-                double rc1 = 0.0;
-                if (f == 1) {
-                    rc1 = __ldg(rcp + 1);
-#pragma unroll
-                    for (int m = 0; m < ZK / 2; ++m)
-                        ufp[m] = uf_early ? uf_pc[m] : __ldcg(reinterpret_cast<const double2*>(D.f[0].filt_old + sbase) + lane + 32 * m);
-                }
-                const bool sra = f == 0 && blend;                                                   // get_rho_T_fluc, df.cpp:474-481
-                double rc4 = 0.0, rc5 = 0.0, rc6 = 0.0;
-                if (sra) { rc4 = __ldg(rcp + 4); rc5 = __ldg(rcp + 5); rc6 = __ldg(rcp + 6); }
-                double2* g_fold = reinterpret_cast<double2*>(F.filt_old + sbase) + lane;
-                double2* g_fluc = reinterpret_cast<double2*>(F.fluc + sbase) + lane;
-                double2* g_T = reinterpret_cast<double2*>(D.T_fluc + sbase) + lane;
-                double2* g_rho = reinterpret_cast<double2*>(D.rho_fluc + sbase) + lane;
-#pragma unroll
-                for (int m = 0; m < ZK / 2; ++m) {
-                    double2 z = zp[m];
-                    if (blend) {                                                                     // correlate_fields, df.cpp:415
-                        z.x = epi_blend(fo_pc[m].x, sa, z.x, sb);
-                        z.y = epi_blend(fo_pc[m].y, sa, z.y, sb);
-                    }
-                    g_fold[32 * m] = z;                                                              // filt_old <- filt, df.cpp:440-442
-                    double2 o = make_double2(epi_scale(rc_own, z.x), epi_scale(rc_own, z.y));       // df.cpp:436,438; v.filt term of 437
-                    if (f == 1) { o.x = epi_cross(rc1, ufp[m].x, o.x); o.y = epi_cross(rc1, ufp[m].y, o.y); }   // df.cpp:437
-                    __stcs(g_fluc + 32 * m, o);
-                    if (sra) {
-                        const double tx = __dmul_rn(rc4, o.x), ty = __dmul_rn(rc4, o.y);
-                        __stcs(g_T + 32 * m, make_double2(__dmul_rn(tx, rc5), __dmul_rn(ty, rc5)));
-                        __stcs(g_rho + 32 * m, make_double2(__dmul_rn(-tx, rc6), __dmul_rn(-ty, rc6)));
-                    }
-                }
-#else
+            }
             if (coalesced) {
                 // Lane l owns line l (its ZK cells) of a 32-line scratch tile; global memory wants piece
                 // p = lane + 32 m.  Both views are conflict-free under the same XOR swizzle.
@@ -843,8 +741,7 @@ __global__ void __maxnreg__(MODE == 1 ? Z_REC_MAXNREG : 168) zsweep_epilogue_ker
                 if (f == 1) {
                     const double rc1 = __ldg(rcp + 1);
                     double uf[ZK];
-                    if (uf_early) { put_pieces(uf_pc); __syncwarp(); get_own(uf); __syncwarp(); }
-                    else load_strip(D.f[0].filt_old + sbase, uf);
+                    load_strip(D.f[0].filt_old + sbase, uf);
 #pragma unroll
                     for (int i = 0; i < ZK; ++i) o[i] = epi_cross(rc1, uf[i], o[i]);            // df.cpp:437
                 }
@@ -859,7 +756,6 @@ __global__ void __maxnreg__(MODE == 1 ? Z_REC_MAXNREG : 168) zsweep_epilogue_ker
                     for (int i = 0; i < ZK; ++i) t[i] = __dmul_rn(-z[i], rc6);
                     store_strip(D.rho_fluc + sbase, t, true);
                 }
-#endif
             } else if (active) {
                 double* __restrict__ fold = F.filt_old + base;
                 double* __restrict__ fluc = F.fluc + base;
@@ -883,12 +779,9 @@ __global__ void __maxnreg__(MODE == 1 ? Z_REC_MAXNREG : 168) zsweep_epilogue_ker
                 }
             }
             if (f == 0) {
-                if (Z_DEFER_PUBLISH) pend_flag = flag_idx;    // this strip's blended u field is on its way to global memory: publish later
-                else {
-                    __threadfence();
-                    __syncwarp();
-                    if (lane == 0) *reinterpret_cast<volatile int*>(P.flags + flag_idx) = P.stamp;
-                }
+                __threadfence();          // publish: this strip's blended u field is in global memory
+                __syncwarp();
+                if (lane == 0) *reinterpret_cast<volatile int*>(P.flags + flag_idx) = P.stamp;
             }
             __syncwarp();                // scratch reads are done before the buffer is refilled by the next-but-one unit
         }
@@ -905,11 +798,6 @@ __global__ void __maxnreg__(MODE == 1 ? Z_REC_MAXNREG : 168) zsweep_epilogue_ker
             atomicAdd(P.prof + 4, 1ull);
         }
         if (!have_next) {
-            if (pend_flag >= 0) {
-                __threadfence();
-                __syncwarp();
-                if (lane == 0) *reinterpret_cast<volatile int*>(P.flags + pend_flag) = P.stamp;
-            }
             if (lane == 0) tl_stamp(P.tl, 1);
             if ((P.debug & 64) && lane == 0) {
                 unsigned long long gt;
@@ -927,10 +815,6 @@ __global__ void __maxnreg__(MODE == 1 ? Z_REC_MAXNREG : 168) zsweep_epilogue_ker
         }
         // descriptor of unit n+2 into the slot unit n just vacated
         int* dfree = descs + (n & 1) * 8;
-        if (!Z_DESC_EARLY) {
-            nn = __shfl_sync(0xffffffffu, claim, 0);
-            if (nn < P.n_units && lane < 8) dreg = __ldg(reinterpret_cast<const int*>(P.units + nn) + lane);
-        }
         if (nn < P.n_units && lane < 8) dfree[lane] = dreg;
         __syncwarp();
         nxt = nn;
@@ -981,12 +865,6 @@ cudaError_t launch_noise(const NoiseParams& P, const PlaneDev& D, cudaStream_t s
     if (P.n_arrays == 0) return cudaSuccess;
     int max_seg = 0;
     for (int a = 0; a < P.n_arrays; ++a) max_seg = P.a[a].n_seg > max_seg ? P.a[a].n_seg : max_seg;
-    if (P.resident_ctas > 0) {
-        NoiseParams Q = P;
-        Q.max_seg = max_seg;
-        noise_kernel<<<(unsigned)P.resident_ctas, NOISE_THREADS, 0, st>>>(Q, D);
-        return cudaGetLastError();
-    }
     dim3 grid((unsigned)P.chunks, (unsigned)max_seg, (unsigned)P.n_arrays);
     noise_kernel<<<grid, NOISE_THREADS, 0, st>>>(P, D);
     return cudaGetLastError();
@@ -1012,14 +890,9 @@ size_t ysweep_smem_bytes() { return sizeof(YSmem<Y_RC, Y_NS>); }
 int noise_threads() { return NOISE_THREADS * NOISE_PAIRS; }
 int ysweep_rc() { return Y_RC; }
 
-static size_t y_pad_smem() {      // experiment (DFB_Y_PAD_SMEM bytes): fewer resident y-sweep CTAs per SM
-    static const size_t pad = std::getenv("DFB_Y_PAD_SMEM") ? (size_t)std::atoi(std::getenv("DFB_Y_PAD_SMEM")) : 0;
-    return pad;
-}
-
 cudaError_t ysweep_prepare() {
     cudaError_t e = cudaFuncSetAttribute(ysweep_tma_kernel<Y_RC, Y_NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)(sizeof(YSmem<Y_RC, Y_NS>) + y_pad_smem()));
+                                         (int)sizeof(YSmem<Y_RC, Y_NS>));
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(ysweep_tma_kernel<Y_RC, Y_NS>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                 cudaSharedmemCarveoutMaxShared);
@@ -1036,7 +909,7 @@ static cudaLaunchConfig_t pdl_config(unsigned grid, unsigned block, size_t smem,
 
 cudaError_t launch_ysweep_tma(const YMaps& maps, const YParams& P, int n_tiles, cudaStream_t st) {
     cudaLaunchAttribute attr;
-    cudaLaunchConfig_t cfg = pdl_config((unsigned)n_tiles, 160, sizeof(YSmem<Y_RC, Y_NS>) + y_pad_smem(), st, &attr);
+    cudaLaunchConfig_t cfg = pdl_config((unsigned)n_tiles, 160, sizeof(YSmem<Y_RC, Y_NS>), st, &attr);
     return cudaLaunchKernelEx(&cfg, ysweep_tma_kernel<Y_RC, Y_NS>, maps, P);
 }
 

@@ -6,7 +6,11 @@ os.environ["DFB_TIMELINE"] = "1"
 import _dfb_import, digital_filtering_b200 as dfb
 from digital_filtering_b200 import workloads as W
 name = sys.argv[1] if len(sys.argv) > 1 else "1024x2048_profile_N128"
-df = dfb.DIGITAL_FILTER(dfb.DFConfig.from_plane(W.NAMED[name](), seed=1), fetch=False)
+if name == "default":
+    df = dfb.DIGITAL_FILTER(dfb.DFConfig(vel_fluc_file=os.path.join(ROOT, "oracle/_ref/files/RST.dat"), line_file=os.path.join(ROOT, "oracle/_ref/line.dat"), seed=1), fetch=False)
+else:
+    df = dfb.DIGITAL_FILTER(dfb.DFConfig.from_plane(W.NAMED[name](), seed=1), fetch=False)
+print(name, "Ny x Nz", df.Ny, df.Nz, "Ny_max", [df.info(0, f) for f in range(3)], "Nz_max", [df.info(1, f) for f in range(3)])
 L = dfb.lib(); L.dfb_debug_timeline.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
 out = (ctypes.c_uint64 * 512)()
 for _ in range(20): df.filter(1e-7)
