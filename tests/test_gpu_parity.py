@@ -101,6 +101,20 @@ def test_G2_saturated_plane(dfb, O, W, variant):
     inject_and_step(dfb, O, W.plane_saturated(48, 600, 32), variant, seed=6, dts=[3e-7])
 
 
+@pytest.mark.parametrize("zmode", ["1", "0"], ids=["z-recursive", "z-direct"])
+def test_G2_both_forms_of_the_z_sweep(dfb, O, W, monkeypatch, zmode):
+    """The tuned z-sweep has two forms: the recursive evaluation of the exponential window (default) and the
+    direct Toeplitz sum (slabs cut off a 16-column boundary, N = 0 rows, DFB_Z_MODE=0).  Both must pass the same gate, at N = 128
+    and on a plane wide enough for several 512-column strips; the recursive form must also stay well inside it (1e-13)."""
+    monkeypatch.setenv("DFB_Z_MODE", zmode)
+    plane = W.plane_profile(72, 1100, 128, 128)
+    df = dfb.DIGITAL_FILTER(dfb.DFConfig.from_plane(plane, noise_mode=dfb.NOISE_INJECT))
+    assert df.tuned and df.info(7) == int(zmode)
+    df.close()
+    worst = inject_and_step(dfb, O, plane, 0, seed=15, dts=[2e-7, 1e-6])
+    assert max(worst.values()) < 1e-13, worst
+
+
 def test_G2_ragged_per_cell_half_widths(dfb, O, W):
     plane = W.plane_ragged(48, 64, 12, seed=3)
     cfg = dfb.DFConfig.from_plane(plane, noise_mode=dfb.NOISE_INJECT)
