@@ -204,6 +204,7 @@ def run_b200(args, plane):
     dist = None
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version banner / warnings: not on stdout, where ONE JSON line goes
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
