@@ -265,7 +265,11 @@ void build_device(dfb_filter_s& H) {
         {
             // outputs per lane: 16 (fewest LDS per DFMA) unless the plane is narrower than one 512-column strip
             const char* zk_env = std::getenv("DFB_ZK");
-            const int ZKc = zk_env ? std::atoi(zk_env) : (P.NzG >= 384 ? 16 : 8);    // by the PLANE's width: slabs then share the plane's lane blocking
+            int nzmax_all = 0;
+            for (int f = 0; f < 3; ++f) nzmax_all = std::max(nzmax_all, P.f[f].Nz_max);
+            // by the PLANE's width and largest N_z (never the slab's): slabs then share the plane's lane blocking.  Short windows
+            // (default reference plane: N_z <= 6) are latency-bound: 256-column units give twice as many of them (0.036 -> 0.017 ms).
+            const int ZKc = zk_env ? std::atoi(zk_env) : ((P.NzG >= 384 && nzmax_all >= 24) ? 16 : 8);
             if (ZKc != 8 && ZKc != 16) throw Error{DFB_ERR_ARG, "DFB_ZK must be 8 or 16"};
             const int strip = 32 * ZKc;
             Z.zk = ZKc;
@@ -359,7 +363,7 @@ void build_device(dfb_filter_s& H) {
             // The recursive form is bound by shared-memory traffic and latency, not by the fp64 pipe: two CTAs per SM run it as
             // fast as three would in the step as a whole, because the third's registers go to the next step's noise CTAs, which
             // then run beside the sweep instead of after it (measured: 0.168 vs 0.176 ms/step on 1024x2048 profile).
-            if (Z.zmode == 1) zb = std::min(zb, 2);
+            if (Z.zmode == 1 && Z.zk == 16) zb = std::min(zb, 2);
             if (std::getenv("DFB_Z_BLOCKS_PER_SM")) zb = std::min(std::max(zb, 3), std::atoi(std::getenv("DFB_Z_BLOCKS_PER_SM")));
             Z.nblocks = std::max(1, std::min(std::max(zb, 1) * prop.multiProcessorCount, (Z.n_units + 3) / 4));
             Z.n_sm = prop.multiProcessorCount;
