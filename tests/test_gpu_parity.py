@@ -455,6 +455,20 @@ def test_large_half_widths_beyond_128(dfb, O, W):
     assert _run_explicit(dfb, O, plane, seed=13, dts=[3e-7])
 
 
+@pytest.mark.parametrize("zk", ["8", "16"])
+def test_recursive_z_sweep_every_window_geometry(dfb, O, W, monkeypatch, zk):
+    """The recursive z-sweep has separate code for even / odd distance to the first tap, windows inside / beyond 64 lines, 64- and
+    128-byte lines and partial last strips: one row per half-width covers them all, against the oracle."""
+    monkeypatch.setenv("DFB_ZK", zk)
+    monkeypatch.setenv("DFB_Z_MODE", "1")
+    Ns = [1, 2, 3, 4, 7, 8, 9, 15, 16, 17, 24, 31, 32, 33, 63, 64, 65, 127, 128, 129, 255, 256, 257, 300]
+    Ny, Nz = len(Ns), 601                                          # 601: partial last strip, odd width
+    Nzr = [np.array(Ns), np.array(Ns[::-1]), np.array(Ns)]
+    Nyr = [np.full(Ny, 3), np.full(Ny, 2), np.full(Ny, 5)]
+    plane = _explicit_plane(W, Ny, Nz, Nyr, Nzr)
+    assert _run_explicit(dfb, O, plane, seed=19, dts=[2e-7, 5e-7])
+
+
 @pytest.mark.parametrize("shape", [(3, 5), (9, 17), (8, 16), (65, 1)])
 def test_tiny_and_awkward_shapes(dfb, O, W, shape):
     Ny, Nz = shape
