@@ -74,6 +74,7 @@ def lib():
         L.dfb_get_table.argtypes = [C.c_void_p, C.c_int, C.c_int, c_dp, C.c_int]
         L.dfb_get_half_widths.argtypes = [C.c_void_p, C.c_int, C.c_int, c_ip]
         L.dfb_filter.argtypes = [C.c_void_p, C.c_double]
+        L.dfb_scatter_to_cells.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
         L.dfb_filter_to_host.argtypes = [C.c_void_p, C.c_double] + [C.c_void_p] * 5
         L.dfb_filter_batch.argtypes = [C.c_void_p, C.c_int, c_dp, C.c_void_p]
         L.dfb_get_field.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
@@ -284,6 +285,13 @@ class DIGITAL_FILTER:
         v.__cuda_array_interface__ = dict(shape=(self.Ny, self.Nz), typestr="<f8", data=(self.device_ptr(which), False),
                                           version=3, strides=None)
         return torch.as_tensor(v, device=torch.device("cuda", self._device))
+
+    def scatter_to_cells(self, which, plane_index, dst_index, dst, mean=None, scale=1.0):
+        """CFD hand-off on the device (dfb_scatter_to_cells): dst[dst_index[i]] = (mean[i] | dst[dst_index[i]]) + scale * field[plane_index[i]].
+        Arguments are CUDA torch tensors (int32 indices, float64 values) on this handle's device."""
+        n = int(plane_index.numel())
+        _check(lib().dfb_scatter_to_cells(self._h, which, n, C.c_void_p(plane_index.data_ptr()), C.c_void_p(dst_index.data_ptr()),
+                                          C.c_void_p(mean.data_ptr()) if mean is not None else None, C.c_double(scale), C.c_void_p(dst.data_ptr())))
 
     def stream(self):
         p = C.c_void_p()

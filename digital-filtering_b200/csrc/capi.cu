@@ -726,6 +726,17 @@ int dfb_device_ptr(dfb_handle h, int which, void** ptr) {
     return DFB_OK;
 }
 
+int dfb_scatter_to_cells(dfb_handle h, int which, int n, const int* plane_index, const int* dst_index, const double* mean, double scale,
+                         double* dst) {
+    if (!h || n < 0 || (n > 0 && (!plane_index || !dst_index || !dst))) return fail(DFB_ERR_ARG, "bad argument");
+    const double* p = field_ptr(*h, which);
+    if (!p) return fail(DFB_ERR_ARG, "unknown field selector");
+    return guarded([&] {
+        CUDA_TRY(cudaSetDevice(h->device));
+        CUDA_TRY(launch_scatter(p, n, plane_index, dst_index, mean, scale, dst, h->stream));
+    });
+}
+
 int dfb_stream(dfb_handle h, void** stream) {
     if (!h || !stream) return fail(DFB_ERR_ARG, "handle/stream is NULL");
     *stream = h->stream;

@@ -836,6 +836,24 @@ __global__ void __launch_bounds__(256) stats_kernel(const PlaneDev D, double* __
     sums[5 * n + i] = __dadd_rn(sums[5 * n + i], __dmul_rn(u, v));
 }
 
+// N3: CFD hand-off (ghost cell = mean + fluctuation, the loop a US3D-style plugin runs over its inflow faces, us3d_user.f90:88-113)
+__global__ void __launch_bounds__(256) scatter_kernel(const double* __restrict__ field, int n, const int* __restrict__ plane_index,
+                                                      const int* __restrict__ dst_index, const double* __restrict__ mean, double scale,
+                                                      double* __restrict__ dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int d = dst_index[i];
+    const double base = mean ? mean[i] : dst[d];
+    dst[d] = __fma_rn(scale, field[plane_index[i]], base);
+}
+
+cudaError_t launch_scatter(const double* field, int n, const int* plane_index, const int* dst_index, const double* mean, double scale,
+                           double* dst, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(field, n, plane_index, dst_index, mean, scale, dst);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_stats(const PlaneDev& D, double* sums, cudaStream_t st) {
     const size_t n = (size_t)D.Ny * D.W;
     stats_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(D, sums, n);

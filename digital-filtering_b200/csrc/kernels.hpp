@@ -15,6 +15,8 @@ cudaError_t launch_ysweep_tma(const YMaps& maps, const YParams& P, int n_items, 
 cudaError_t zsweep_prepare(int zk, int mode, size_t smem, int* blocks_per_sm);
 cudaError_t launch_zsweep_tuned(const ZMaps& maps, const ZParams& P, cudaStream_t st);
 cudaError_t launch_stats(const PlaneDev& D, double* sums, cudaStream_t st);
+cudaError_t launch_scatter(const double* field, int n, const int* plane_index, const int* dst_index, const double* mean, double scale,
+                           double* dst, cudaStream_t st);
 cudaError_t launch_dfma_peak(double* out, int blocks, int iters, cudaStream_t st);
 
 }  // namespace dfb

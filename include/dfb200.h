@@ -127,6 +127,12 @@ int dfb_get_field(dfb_handle h, int which, double* dst, int dst_on_device);
 int dfb_device_ptr(dfb_handle h, int which, void** ptr);
 /* the handle's cudaStream_t */
 int dfb_stream(dfb_handle h, void** stream);
+/* CFD hand-off on the device (the call a US3D-style plugin makes per inflow face, us3d_user.f90:88-113:
+ * ghost-cell state = mean + fluctuation): dst[dst_index[i]] = mean[i] (or dst's own value when mean is NULL) +
+ * scale * field[plane_index[i]], i < n, enqueued on the handle's stream after the step that produced `which`.
+ * All four pointers are DEVICE pointers; plane_index is j*Nz + k within this handle's slab. */
+int dfb_scatter_to_cells(dfb_handle h, int which, int n, const int* plane_index, const int* dst_index,
+                         const double* mean, double scale, double* dst);
 int dfb_sync(dfb_handle h);
 
 /* noise injection ("ingest the reference's own draws").  Host arrays in the

@@ -526,3 +526,31 @@ def test_G3_config1_default_plane_100_steps(dfb, O):
         rel = np.abs(acc[i][ok_rows] - tgt[ok_rows]) / tgt[ok_rows]
         assert np.median(rel) < 0.03 and np.percentile(rel, 95) < 0.08, (i, float(np.median(rel)), float(np.percentile(rel, 95)))
     df.close()
+
+
+def test_N3_device_scatter_to_cfd_ghost_cells(dfb, W):
+    """the loop a US3D-style plugin runs over its inflow faces (ghost cell = mean + fluctuation,
+    us3d_user.f90:88-113), on the device through dfb_scatter_to_cells, against numpy."""
+    import torch
+    plane = W.plane_profile(40, 96, 8, 6)
+    df = dfb.DIGITAL_FILTER(dfb.DFConfig.from_plane(plane, seed=31))
+    df.filter(1e-7)
+    rng = np.random.default_rng(2)
+    nfaces = 40 * 96
+    face_cell = rng.permutation(nfaces).astype(np.int32)            # inflow face i looks at plane cell face_cell[i]
+    ghost = (rng.permutation(3 * nfaces)[:nfaces]).astype(np.int32)  # ... and owns CFD cell ghost[i]
+    u0 = rng.normal(869.1, 1.0, nfaces)
+    u_cfd = rng.normal(0.0, 1.0, 3 * nfaces)
+    t_cfd = u_cfd.copy()
+    d_u, d_t = torch.from_numpy(u_cfd).cuda(), torch.from_numpy(t_cfd).cuda()
+    pi, gi, mu = torch.from_numpy(face_cell).cuda(), torch.from_numpy(ghost).cuda(), torch.from_numpy(u0).cuda()
+    df.scatter_to_cells(dfb.U_FLUC, pi, gi, d_u, mean=mu)             # u(ii) = u0 + u'
+    df.scatter_to_cells(dfb.T_FLUC, pi, gi, d_t, mean=None, scale=2.0)   # t(ii) += 2 T'
+    df.sync()
+    exp_u = u_cfd.copy(); exp_u[ghost] = u0 + df.u.fluc.ravel()[face_cell]
+    exp_t = t_cfd.copy(); exp_t[ghost] = t_cfd[ghost] + 2.0 * df.T_fluc.ravel()[face_cell]
+    assert np.array_equal(d_u.cpu().numpy(), exp_u)
+    assert np.allclose(d_t.cpu().numpy(), exp_t, rtol=0, atol=1e-15 * np.abs(exp_t).max())
+    with pytest.raises(dfb.DfbError):
+        df.scatter_to_cells(99, pi, gi, d_u)
+    df.close()
