@@ -73,6 +73,7 @@ struct dfb_filter_s {
     YMaps maps[2]{};
     YParams yp[2]{};
     int n_items = 0;
+    int n_tiles_dense = 0, n_tiles_rec = 0;   // y-sweep tiles: dense band-matrix tiles first, then recursive tiles
     // tuned z-sweep
     ZParams zp[2]{};
     ZMaps zmaps[2]{};
@@ -198,45 +199,121 @@ void build_device(dfb_filter_s& H) {
         std::vector<YGroup> groups;
         std::vector<YTile> tiles;
         std::vector<double> cmat;
+        // Row groups.  The reference's coefficients are b_i = a^|i| / s (df.cpp:168-177): a group whose rows all have the same
+        // half-width N >= 16 is evaluated recursively (ysweep_rec_kernel: ~1 FMA per input row and column instead of 8); the
+        // others keep the dense band matrix.  N_y changes every few rows on boundary-layer grids, so groups follow the runs of
+        // equal N: whole groups of YJ rows out of a run, a tail of >= 4 rows as a short group, shorter leftovers merged into a
+        // mixed (dense) group with their neighbours.  DFB_Y_MODE=0: fixed groups of YJ rows, all dense.
+        constexpr int Y_REC_MIN_N = 16;
+        // The recursive form streams the same windows as the dense one but does ~6x less arithmetic on them, so it runs at the
+        // L2 -> SM streaming rate; it wins where (nearly) all of the y work sits in long runs of one N >= 16 (uniform planes:
+        // 0.223 -> 0.166 ms/step at 1024x2048, N = 128) and loses on boundary-layer grids whose N_y changes every few rows
+        // (0.143 -> 0.166: more, shorter groups, each with its whole window).  Default: on when >= 90 % of the y taps lie in runs
+        // of >= 16 equal half-widths >= 16; DFB_Y_MODE=1 / 0 forces it on / off.
+        bool yrec_on;
+        {
+            double taps_all = 0, taps_long = 0;
+            for (int f = 0; f < 3; ++f) {
+                const std::vector<int>& Nr = P.f[f].N_y_row;
+                for (int j = 0; j < Ny;) {
+                    int r = 1;
+                    while (j + r < Ny && Nr[j + r] == Nr[j]) ++r;
+                    const double w = (double)r * (2.0 * Nr[j] + 1.0);
+                    taps_all += w;
+                    if (r >= 16 && Nr[j] >= Y_REC_MIN_N) taps_long += w;
+                    j += r;
+                }
+            }
+            yrec_on = taps_long >= 0.9 * taps_all;
+            if (const char* ym = std::getenv("DFB_Y_MODE")) yrec_on = std::atoi(ym) != 0;
+        }
+        std::vector<char> yrec_need(P.coef.Nmax + 1, 0);
+        std::vector<YTile> tiles_dense, tiles_rec;
         for (int f = 0; f < 3; ++f) {
             const FieldPlan& FP = P.f[f];
-            const int first_group = (int)groups.size();
-            for (int j0 = 0; j0 < Ny; j0 += YJ) {
+            std::vector<YGroup> gk[2];        // [0] dense (mixed half-widths or small N), [1] recursive, each in row order
+            auto run_len = [&](int j) { int r = 1; while (j + r < Ny && FP.N_y_row[j + r] == FP.N_y_row[j]) ++r; return r; };
+            for (int j0 = 0; j0 < Ny;) {
                 YGroup g{};
-                g.field = f; g.j0 = j0; g.nrows = std::min(YJ, Ny - j0);
+                int nr;
+                bool uniform = false;
+                const int R = run_len(j0);
+                if (yrec_on && FP.N_y_row[j0] >= Y_REC_MIN_N && R >= 4) { nr = std::min(R, YJ); uniform = true; }
+                else {
+                    // mixed group: up to YJ rows, but stop in front of a run long enough to be worth its own recursive groups
+                    nr = 0;
+                    while (nr < YJ && j0 + nr < Ny) {
+                        const int r2 = run_len(j0 + nr);
+                        if (yrec_on && nr > 0 && FP.N_y_row[j0 + nr] >= Y_REC_MIN_N && r2 >= YJ) break;
+                        nr += std::min(r2, YJ - nr);
+                    }
+                }
+                g.field = f; g.j0 = j0; g.nrows = nr;
                 g.Nmax = 0;
                 for (int jj = 0; jj < g.nrows; ++jj) g.Nmax = std::max(g.Nmax, FP.N_y_row[j0 + jj]);
                 // padded input rows touched: output row j0+jj, tap i -> row j0 + jj + Ny_max + i  (df.cpp:362,374)
                 const int lo = j0 + FP.Ny_max - g.Nmax, hi = j0 + g.nrows - 1 + FP.Ny_max + g.Nmax;
                 g.cstart = lo / RC;
                 g.nchunks = hi / RC + 1 - g.cstart;
-                g.cmat_off = (long long)cmat.size();
-                cmat.resize(cmat.size() + (size_t)g.nchunks * RC * YJ, 0.0);
-                double* cm = cmat.data() + g.cmat_off;
-                for (int jj = 0; jj < g.nrows; ++jj) {
-                    const int N = FP.N_y_row[j0 + jj];
-                    const double* b = P.coef.centre(N);
-                    for (int i = -N; i <= N; ++i)
-                        cm[(size_t)(j0 + jj + FP.Ny_max + i - g.cstart * RC) * YJ + jj] = b[i];
+                g.rec = uniform ? 1 : 0;
+                g.w0 = lo;
+                if (g.rec) {
+                    g.cmat_off = -1;
+                    yrec_need[g.Nmax] = 1;
+                } else {
+                    g.cmat_off = (long long)cmat.size();
+                    cmat.resize(cmat.size() + (size_t)g.nchunks * RC * YJ, 0.0);
+                    double* cm = cmat.data() + g.cmat_off;
+                    for (int jj = 0; jj < g.nrows; ++jj) {
+                        const int N = FP.N_y_row[j0 + jj];
+                        const double* b = P.coef.centre(N);
+                        for (int i = -N; i <= N; ++i)
+                            cm[(size_t)(j0 + jj + FP.Ny_max + i - g.cstart * RC) * YJ + jj] = b[i];
+                    }
                 }
-                groups.push_back(g);
+                gk[g.rec].push_back(g);
+                j0 += nr;
             }
-            const int ng = (int)groups.size() - first_group;
-            for (int gb = 0; gb < ng; gb += Y_G) {
-                YTile t{};
-                t.field = f; t.g0 = first_group + gb; t.ngroups = std::min(Y_G, ng - gb);
-                t.cbegin = 1 << 30; t.cend = 0;
-                for (int w = 0; w < t.ngroups; ++w) {
-                    const YGroup& g = groups[t.g0 + w];
-                    t.cbegin = std::min(t.cbegin, g.cstart);
-                    t.cend = std::max(t.cend, g.cstart + g.nchunks);
+            // tiles: up to Y_G groups of the same kind, neighbours in row order (not necessarily adjacent rows), share one sample stream
+            for (int kind = 0; kind < 2; ++kind) {
+                const int first_group = (int)groups.size();
+                groups.insert(groups.end(), gk[kind].begin(), gk[kind].end());
+                const int ng = (int)gk[kind].size();
+                for (int gb = 0; gb < ng; gb += Y_G) {
+                    YTile t{};
+                    t.field = f; t.g0 = first_group + gb; t.ngroups = std::min(Y_G, ng - gb);
+                    t.cbegin = 1 << 30; t.cend = 0;
+                    for (int w = 0; w < t.ngroups; ++w) {
+                        const YGroup& g = groups[t.g0 + w];
+                        t.cbegin = std::min(t.cbegin, g.cstart);
+                        t.cend = std::max(t.cend, g.cstart + g.nchunks);
+                    }
+                    for (int c0 = 0; c0 < D.f[f].We; c0 += Y_TK) { t.col0 = c0; (kind ? tiles_rec : tiles_dense).push_back(t); }
                 }
-                for (int c0 = 0; c0 < D.f[f].We; c0 += Y_TK) { t.col0 = c0; tiles.push_back(t); }
             }
         }
-        std::stable_sort(tiles.begin(), tiles.end(), [](const YTile& a, const YTile& b) {
-            return (a.cend - a.cbegin) > (b.cend - b.cbegin);   // longest first
-        });
+        auto longest_first = [](const YTile& a, const YTile& b) { return (a.cend - a.cbegin) > (b.cend - b.cbegin); };
+        std::stable_sort(tiles_dense.begin(), tiles_dense.end(), longest_first);
+        std::stable_sort(tiles_rec.begin(), tiles_rec.end(), longest_first);
+        H.n_tiles_dense = (int)tiles_dense.size();
+        H.n_tiles_rec = (int)tiles_rec.size();
+        tiles = tiles_dense;
+        tiles.insert(tiles.end(), tiles_rec.begin(), tiles_rec.end());
+        {
+            // per half-width: a, -a^(N+1), 1/s, a^-1 .. a^-7, a^2, a^4, a^8
+            std::vector<double> yrec((size_t)(P.coef.Nmax + 1) * 16, 0.0);
+            for (int N = 1; N <= P.coef.Nmax; ++N) {
+                if (!yrec_need[N]) continue;
+                double* q = yrec.data() + (size_t)N * 16;
+                const long double a = (long double)std::exp(-2.0 * 3.14159265358979323846 * 1.0 / N);
+                q[0] = (double)a;
+                q[1] = -(double)std::pow(a, (long double)(N + 1));
+                q[2] = *P.coef.centre(N);
+                for (int t = 1; t < 8; ++t) q[2 + t] = (double)std::pow(a, (long double)(-t));
+                q[10] = (double)(a * a); q[11] = (double)std::pow(a, 4.0L); q[12] = (double)std::pow(a, 8.0L);
+            }
+            H.yp[0].yrec = H.upload(yrec);
+        }
         H.yp[0].groups = H.upload(groups);
         H.yp[0].tiles = H.upload(tiles);
         H.yp[0].cmat = H.upload(cmat);
@@ -479,7 +556,7 @@ void run_step(dfb_filter_s& H, double dt, bool first) {
     if (H.timing) CUDA_TRY(cudaEventRecord(H.ev[1], H.stream));
     if (H.noise_mode == DFB_NOISE_GENERATE && H.ybuf_step[b] == H.step) {
         // this step's y-sweep already ran (or is running) on the side stream; ev_noise[b] above covers it
-    } else if (H.tuned) CUDA_TRY(launch_ysweep_tma(H.maps[b], H.yp[b], H.n_items, H.stream));
+    } else if (H.tuned) CUDA_TRY(launch_ysweep_tma(H.maps[b], H.yp[b], H.n_tiles_dense, H.n_tiles_rec, H.stream));
     else CUDA_TRY(launch_ysweep_simple(H.D[b], H.stream));
     if (H.timing) CUDA_TRY(cudaEventRecord(H.ev[2], H.stream));
     StepConsts S{};
@@ -506,7 +583,7 @@ void run_step(dfb_filter_s& H, double dt, bool first) {
         // ... and so does its y-sweep (it reads only that noise and writes only that set's r_zs interior): it
         // becomes resident as this step's z-sweep CTAs retire and keeps the fp64 pipe busy through the tail.
         if (H.tuned && H.y_ahead) {
-            CUDA_TRY(launch_ysweep_tma(H.maps[nb], H.yp[nb], H.n_items, H.side));
+            CUDA_TRY(launch_ysweep_tma(H.maps[nb], H.yp[nb], H.n_tiles_dense, H.n_tiles_rec, H.side));
             CUDA_TRY(cudaEventRecord(H.ev_noise[nb], H.side));      // "set nb is ready" now means noise + y-sweep
             H.ybuf_step[nb] = H.step;
         }

@@ -57,7 +57,9 @@ struct YGroup {                // YJ consecutive output rows of one field
     int field, j0, nrows, Nmax;
     int cstart;                // first chunk of the window on the field's absolute chunk grid (chunk c = padded rows [c*RC, (c+1)*RC))
     int nchunks;               // chunks the window touches
-    long long cmat_off;        // doubles, into the band-matrix pool: Cmat[(row - cstart*RC)][YJ]
+    long long cmat_off;        // doubles, into the band-matrix pool: Cmat[(row - cstart*RC)][YJ]; -1: recursive group (no matrix)
+    int rec;                   // 1: every row has the same half-width N = Nmax >= 16: recursive evaluation (ysweep_rec_kernel)
+    int w0;                    // padded row of the group's first window sample (= j0 + Ny_max - Nmax)
 };
 struct YTile {                 // up to Y_G consecutive groups x Y_TK columns
     int field, col0, g0, ngroups;
@@ -99,6 +101,8 @@ struct YParams {
     const YTile* tiles;
     const double* cmat;
     int* zcounter;             // work counter of the z-sweep that follows (reset here)
+    const double* yrec;        // recursive groups, 16 doubles per half-width N: a, -a^(N+1), 1/s, a^-1 .. a^-7, a^2, a^4, a^8
+    int tile0;                 // first tile of this launch in `tiles` (dense tiles first, then recursive tiles)
     unsigned long long* prof;  // [8] cycle counters (development probe, filled when debug != 0)
     unsigned long long* tl;    // development aid (DFB_TIMELINE), see NoiseParams
     int debug;

@@ -11,7 +11,8 @@ size_t ysweep_smem_bytes();
 int noise_threads();          // CTA size of noise_kernel (NoiseParams::chunks = ceil(max_np / noise_threads()))
 int ysweep_rc();
 cudaError_t ysweep_prepare();
-cudaError_t launch_ysweep_tma(const YMaps& maps, const YParams& P, int n_items, cudaStream_t st);
+// dense band-matrix tiles [0, n_dense) with ysweep_tma_kernel, then recursive tiles [n_dense, n_dense + n_rec) with ysweep_rec_kernel
+cudaError_t launch_ysweep_tma(const YMaps& maps, const YParams& P, int n_dense, int n_rec, cudaStream_t st);
 cudaError_t zsweep_prepare(int zk, int mode, size_t smem, int* blocks_per_sm);
 cudaError_t launch_zsweep_tuned(const ZMaps& maps, const ZParams& P, cudaStream_t st);
 cudaError_t launch_stats(const PlaneDev& D, double* sums, cudaStream_t st);

@@ -455,6 +455,25 @@ def test_large_half_widths_beyond_128(dfb, O, W):
     assert _run_explicit(dfb, O, plane, seed=13, dts=[3e-7])
 
 
+@pytest.mark.parametrize("ymode", ["1", "0"], ids=["y-recursive", "y-dense"])
+def test_G2_both_forms_of_the_y_sweep(dfb, O, W, monkeypatch, ymode):
+    """The tuned y-sweep evaluates row groups with one half-width N >= 16 recursively (ysweep_rec_kernel) and everything else with
+    dense band matrices; by default the recursive kernel is only switched on for (nearly) uniform planes.  Forced on and forced
+    off, on a boundary-layer profile (N_y changes every few rows: runs of every length, mixed leftovers) and on hand-made runs
+    (lengths 1..20, N from 2 to 200, windows not aligned to the 8-row chunks), both must pass the gate."""
+    monkeypatch.setenv("DFB_Y_MODE", ymode)
+    worst = inject_and_step(dfb, O, W.plane_profile(200, 300, 96, 24), 0, seed=23, dts=[2e-7, 8e-7])
+    assert max(worst.values()) < 1e-13, worst
+    rng = np.random.default_rng(7)
+    runs, Ns = [], [2, 8, 15, 16, 17, 18, 31, 40, 64, 66, 100, 128, 200]
+    while sum(runs) < 230:
+        runs.append(int(rng.integers(1, 21)))
+    row_N = np.concatenate([np.full(r, Ns[int(rng.integers(0, len(Ns)))]) for r in runs])
+    Ny, Nz = len(row_N), 150
+    plane = _explicit_plane(W, Ny, Nz, [row_N, row_N[::-1].copy(), np.full(Ny, 128)], [np.full(Ny, 4)] * 3)
+    assert _run_explicit(dfb, O, plane, seed=24, dts=[3e-7])
+
+
 @pytest.mark.parametrize("zk", ["8", "16"])
 def test_recursive_z_sweep_every_window_geometry(dfb, O, W, monkeypatch, zk):
     """The recursive z-sweep has separate code for even / odd distance to the first tap, windows inside / beyond 64 lines, 64- and
