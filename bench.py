@@ -296,7 +296,8 @@ def run_b200(args, plane):
     zmode = "recursive" if df.info(7) == 1 else "direct"
     kern = {
         # y-sweep: direct form (dense band matrices): executes exactly the reference's 2*(2N_y+1) flops per cell -> fp64 roof
-        "ysweep_tma_kernel": dict(ms=med["ysweep"], form="direct", tflops=2 * taps_y / (med["ysweep"] * 1e-3) / 1e12),
+        "ysweep_tma_kernel": dict(ms=med["ysweep"], form="direct" if df.info(8) == 0 else "recursive (%d tiles) + direct (%d tiles)" % (df.info(8), df.info(9)),
+                                  tflops=2 * taps_y / (med["ysweep"] * 1e-3) / 1e12),
         # z-sweep + epilogue: in recursive mode it no longer executes the reference's 2*(2N_z+1) flops per cell (about 14x fewer at
         # N = 128): its roof is the memory system; `equivalent_tflops` is the reference-formulation figure, for comparison only
         "zsweep_epilogue_kernel": dict(ms=med["zsweep_epilogue"], form=zmode, equivalent_tflops=2 * taps_z / (med["zsweep_epilogue"] * 1e-3) / 1e12,

@@ -709,6 +709,8 @@ int dfb_info(dfb_handle h, int what, int field, int64_t* out64) {
         case 5: *out64 = h->plan.NzG; break;
         case 6: *out64 = h->device; break;
         case 7: *out64 = h->tuned ? h->zp[0].zmode : 0; break;
+        case 8: *out64 = h->tuned ? h->n_tiles_rec : 0; break;
+        case 9: *out64 = h->tuned ? h->n_tiles_dense : 0; break;
         default: return fail(DFB_ERR_ARG, "unknown info selector");
     }
     return DFB_OK;
