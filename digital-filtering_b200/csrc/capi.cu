@@ -314,6 +314,7 @@ void build_device(dfb_filter_s& H) {
             }
             H.yp[0].yrec = H.upload(yrec);
         }
+        H.yp[0].resident_grid = std::getenv("DFB_Y_PERSIST") ? std::atoi(std::getenv("DFB_Y_PERSIST")) : 0;
         H.yp[0].groups = H.upload(groups);
         H.yp[0].tiles = H.upload(tiles);
         H.yp[0].cmat = H.upload(cmat);

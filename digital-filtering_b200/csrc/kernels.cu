@@ -227,20 +227,24 @@ template <int RC, int NS>
 __global__ void __launch_bounds__(160, 3) ysweep_tma_kernel(const __grid_constant__ YMaps maps, const YParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     YSmem<RC, NS>& sm = *reinterpret_cast<YSmem<RC, NS>*>(smem_raw);
-    const YTile t = P.tiles[P.tile0 + blockIdx.x];
-    const FieldDev& F = P.D.f[t.field];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // One tile per CTA (gridDim.x == n_tiles), or a resident grid whose CTAs walk the (longest-first) tile list with a stride:
+    // with every CTA resident from the start, the block scheduler has nothing of this kernel pending and lets the next step's
+    // noise CTAs (low-priority stream) in beside it.
+    for (int tix = blockIdx.x; tix < P.n_tiles; tix += gridDim.x) {
+    const YTile t = P.tiles[P.tile0 + tix];
+    const FieldDev& F = P.D.f[t.field];
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NS; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], Y_G); }
         mbar_fence_init();
-        if (blockIdx.x == 0 && P.zcounter) *P.zcounter = 0;      // the z-sweep that follows pulls its items from here
+        if (tix == 0 && P.zcounter) *P.zcounter = 0;      // the z-sweep that follows pulls its items from here
         tl_stamp(P.tl, 0);
     }
     __syncthreads();
     // Programmatic dependent launch: everything above overlapped the previous kernel's tail; from here on we touch
     // global data it may have produced (noise) or still read.
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (tix == (int)blockIdx.x) asm volatile("griddepcontrol.wait;" ::: "memory");
 
     if (warp == Y_G) {
         if (lane == 0) {
@@ -269,8 +273,7 @@ __global__ void __launch_bounds__(160, 3) ysweep_tma_kernel(const __grid_constan
                         tma_load_1d(&sm.coefs[s][w][0][0], cm[w] + (long long)(c - cs[w]) * RC * YJ, RC * YJ * sizeof(double), &sm.full[s]);
             }
         }
-        return;
-    }
+    } else {
 
     const bool have = warp < t.ngroups;
     YGroup g{};
@@ -314,7 +317,7 @@ __global__ void __launch_bounds__(160, 3) ysweep_tma_kernel(const __grid_constan
         if (P.debug) tc += clock64() - tb;
     }
     const long long tloop = P.debug ? clock64() : 0;
-    if (!have) return;
+    if (have) {
 
     // r_zs interior (df.cpp:377): extended column x -> logical column x + yshift
     const int xa0 = t.col0 + 2 * lane;
@@ -344,6 +347,10 @@ __global__ void __launch_bounds__(160, 3) ysweep_tma_kernel(const __grid_constan
         atomicAdd(P.prof + 4, 1ull);
         atomicAdd(P.prof + 5, (unsigned long long)(t.cend - t.cbegin));
     }
+    }   // have
+    }   // consumer
+    __syncthreads();        // every warp is done with the ring and its barriers before the next tile re-initialises them
+    }   // tiles
 }
 
 // =================================================================================================
@@ -1107,7 +1114,9 @@ cudaError_t launch_ysweep_tma(const YMaps& maps, const YParams& P, int n_dense, 
     YParams Q = P;
     if (n_dense > 0) {
         Q.tile0 = 0;
-        cudaLaunchConfig_t cfg = pdl_config((unsigned)n_dense, 160, sizeof(YSmem<Y_RC, Y_NS>), st, &attr);
+        Q.n_tiles = n_dense;
+        const int grid = P.resident_grid > 0 ? (n_dense < P.resident_grid ? n_dense : P.resident_grid) : n_dense;
+        cudaLaunchConfig_t cfg = pdl_config((unsigned)grid, 160, sizeof(YSmem<Y_RC, Y_NS>), st, &attr);
         cudaError_t e = cudaLaunchKernelEx(&cfg, ysweep_tma_kernel<Y_RC, Y_NS>, maps, Q);
         if (e != cudaSuccess) return e;
     }
