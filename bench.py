@@ -294,34 +294,43 @@ def run_b200(args, plane):
     hbm_src = "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"
     alg_bytes = 88 * cells                                    # 5 outputs + filt_old r/w x3
     zmode = "recursive" if df.info(7) == 1 else "direct"
+    y_rec = df.info(8) > 0
+    y_bytes = 3 * 16 * cells                                  # y-sweep: r_ys read once, r_zs interior written once, per field
     kern = {
-        # y-sweep: direct form (dense band matrices): executes exactly the reference's 2*(2N_y+1) flops per cell -> fp64 roof
-        "ysweep_tma_kernel": dict(ms=med["ysweep"], form="direct" if df.info(8) == 0 else "recursive (%d tiles) + direct (%d tiles)" % (df.info(8), df.info(9)),
-                                  tflops=2 * taps_y / (med["ysweep"] * 1e-3) / 1e12),
-        # z-sweep + epilogue: in recursive mode it no longer executes the reference's 2*(2N_z+1) flops per cell (about 14x fewer at
-        # N = 128): its roof is the memory system; `equivalent_tflops` is the reference-formulation figure, for comparison only
+        # y-sweep.  Direct form (dense band matrices): executes exactly the reference's 2*(2N_y+1) flops per cell -> fp64 roof.
+        # Recursive form (uniform planes): ~6x fewer flops -> its roof is the memory system; equivalent_tflops = reference-
+        # formulation flops / time, for comparison only.
+        "ysweep_tma_kernel": dict(ms=med["ysweep"], form=("recursive (%d tiles) + direct (%d tiles)" % (df.info(8), df.info(9))) if y_rec else "direct"),
+        # z-sweep + epilogue: in recursive mode it no longer executes the reference's 2*(2N_z+1) flops per cell (about 13x fewer at
+        # N = 128): its roof is the memory system
         "zsweep_epilogue_kernel": dict(ms=med["zsweep_epilogue"], form=zmode, equivalent_tflops=2 * taps_z / (med["zsweep_epilogue"] * 1e-3) / 1e12,
                                        hbm_gbs=alg_bytes / (med["zsweep_epilogue"] * 1e-3) / 1e9),
         "noise_kernel": dict(ms=med["noise"]),
     }
-    kern["ysweep_tma_kernel"]["frac_fp64"] = kern["ysweep_tma_kernel"]["tflops"] / fp64_peak
-    kern["zsweep_epilogue_kernel"]["frac_hbm"] = kern["zsweep_epilogue_kernel"]["hbm_gbs"] / hbm_peak
+    ky, kz = kern["ysweep_tma_kernel"], kern["zsweep_epilogue_kernel"]
+    if y_rec:
+        ky.update(equivalent_tflops=2 * taps_y / (med["ysweep"] * 1e-3) / 1e12, hbm_gbs=y_bytes / (med["ysweep"] * 1e-3) / 1e9)
+        ky["frac_hbm"] = ky["hbm_gbs"] / hbm_peak
+    else:
+        ky.update(tflops=2 * taps_y / (med["ysweep"] * 1e-3) / 1e12)
+        ky["frac_fp64"] = ky["tflops"] / fp64_peak
+    kz["frac_hbm"] = kz["hbm_gbs"] / hbm_peak
     if zmode == "direct":
-        kern["zsweep_epilogue_kernel"]["frac_fp64"] = kern["zsweep_epilogue_kernel"]["equivalent_tflops"] / fp64_peak
+        kz["frac_fp64"] = kz["equivalent_tflops"] / fp64_peak
     step_ms = ms_total / K
     eq_tf = 2 * (taps_y + taps_z) / (step_ms * 1e-3) / 1e12
     step = dict(equivalent_tflops=eq_tf, equivalent_frac_fp64=eq_tf / fp64_peak,
-                note="reference-formulation flops / step time; the recursive z-sweep executes far fewer, so this is a speed-up figure, not a utilisation",
+                note="reference-formulation flops / step time; the recursive sweeps execute far fewer, so this is a speed-up figure, not a utilisation",
                 hbm_gbs=alg_bytes / (step_ms * 1e-3) / 1e9, frac_hbm=alg_bytes / (step_ms * 1e-3) / 1e9 / hbm_peak, hbm_peak=hbm_peak, hbm_peak_source=hbm_src)
     peak_src = "DFMA microbenchmark measured live in this run (dfb_measure_fp64_peak); MEASURED_PEAKS.json has no fp64 entry"
     tsrc = "profiles/ncu_full_r01c_summary.csv (ncu --set full, one launch)"
-    if med["ysweep"] >= med["zsweep_epilogue"] or zmode == "direct":
-        dom = "ysweep_tma_kernel" if med["ysweep"] >= med["zsweep_epilogue"] else "zsweep_epilogue_kernel"
-        roofline = dict(bound="fp64", kernel=dom, achieved=kern[dom].get("tflops", kern[dom].get("equivalent_tflops")), peak=fp64_peak, unit="TFLOP/s",
-                        frac=kern[dom]["frac_fp64"], traffic=ncu_traffic(dom, plane["name"]), traffic_source=tsrc, peak_source=peak_src, step=step, kernels=kern)
+    dom = "ysweep_tma_kernel" if med["ysweep"] >= med["zsweep_epilogue"] else "zsweep_epilogue_kernel"
+    kd = kern[dom]
+    if "frac_fp64" in kd and kd["form"] == "direct":
+        roofline = dict(bound="fp64", kernel=dom, achieved=kd.get("tflops", kd.get("equivalent_tflops")), peak=fp64_peak, unit="TFLOP/s",
+                        frac=kd["frac_fp64"], traffic=ncu_traffic(dom, plane["name"]), traffic_source=tsrc, peak_source=peak_src, step=step, kernels=kern)
     else:
-        dom = "zsweep_epilogue_kernel"
-        roofline = dict(bound="hbm", kernel=dom, achieved=kern[dom]["hbm_gbs"], peak=hbm_peak, unit="GB/s", frac=kern[dom]["frac_hbm"],
+        roofline = dict(bound="hbm", kernel=dom, achieved=kd["hbm_gbs"], peak=hbm_peak, unit="GB/s", frac=kd["frac_hbm"],
                         traffic=ncu_traffic(dom, plane["name"]), traffic_source=tsrc, peak_source=hbm_src, step=step, kernels=kern)
 
     # ---- cpu baseline: the reference's own df.cpp, 1 core, bounded sample ----
