@@ -338,7 +338,7 @@ def run_b200(args, plane):
     if world == 1 and not args.no_cpu:
         try:
             s, _ = sample_plane(plane)
-            nst = 5
+            nst = 25                  # ~10 s of one host core
             secs, kind = cpu_reference_run(s, nst, 1, 1)
             cpu = dict(value=s["Ny"] * s["Nz"] * nst / secs, unit="cell-updates/s", cores=1 if kind == "reference" else (os.cpu_count() or 1), kind=kind,
                        sample=f"{nst} steps of a {s['Ny']}x{s['Nz']} spanwise sub-slab of the {plane['Ny']}x{plane['Nz']} plane (same rows, same half-widths); "
