@@ -1,5 +1,2 @@
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python tools/stepbench.py
-DFB_Y_MODE=1 python tools/stepbench.py 1024x2048_profile_N128 4096x8192_profile_N128
-python tools/stepbench.py 4096x8192_profile_N128 4096x8192_saturated_N128
-python tools/quick_gpu.py 1024x2048_saturated_N128 2>&1 | grep "variant 0" | cut -c1-330
+timeout 900 ncu --set full --import-source on --clock-control none -k regex:"noise_kernel|ysweep_tma|zsweep_epilogue" -s 9 -c 3 -o gpurun_out/full_r01c -f python bench.py --steps 3 --warmup 3 --no-cpu --no-sweep > gpurun_out/ncu_f.log 2>&1
+tail -1 gpurun_out/ncu_f.log | cut -c1-120
