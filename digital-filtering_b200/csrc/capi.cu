@@ -229,6 +229,17 @@ void build_device(dfb_filter_s& H) {
         }
         std::vector<char> yrec_need(P.coef.Nmax + 1, 0);
         std::vector<YTile> tiles_dense, tiles_rec;
+        // columns per dense tile: 64 instead of 128 when 128-column tiles would not even give every SM two CTAs (the reference's
+        // default plane: 192 tiles of up to 57 chunks; y-sweep 0.036 -> 0.026 ms); recursive tiles always take 128
+        int ytk = Y_TK;
+        if (!yrec_on) {
+            long long est = 0;
+            for (int f = 0; f < 3; ++f) est += (long long)((D.f[f].We + Y_TK - 1) / Y_TK) * (((Ny + YJ - 1) / YJ + Y_G - 1) / Y_G);
+            int nymax = 0;
+            for (int f = 0; f < 3; ++f) nymax = std::max(nymax, P.f[f].Ny_max);
+            if (est < 2 * 148 && nymax >= 64) ytk = 64;      // few, very long tiles (measured: 512x512 N <= 32 prefers 128)
+            if (const char* e = std::getenv("DFB_Y_TK")) ytk = std::atoi(e) == 64 ? 64 : Y_TK;
+        }
         for (int f = 0; f < 3; ++f) {
             const FieldPlan& FP = P.f[f];
             std::vector<YGroup> gk[2];        // [0] dense (mixed half-widths or small N), [1] recursive, each in row order
@@ -288,7 +299,8 @@ void build_device(dfb_filter_s& H) {
                         t.cbegin = std::min(t.cbegin, g.cstart);
                         t.cend = std::max(t.cend, g.cstart + g.nchunks);
                     }
-                    for (int c0 = 0; c0 < D.f[f].We; c0 += Y_TK) { t.col0 = c0; (kind ? tiles_rec : tiles_dense).push_back(t); }
+                    const int step = kind ? Y_TK : ytk;
+                    for (int c0 = 0; c0 < D.f[f].We; c0 += step) { t.col0 = c0; (kind ? tiles_rec : tiles_dense).push_back(t); }
                 }
             }
         }
@@ -315,6 +327,7 @@ void build_device(dfb_filter_s& H) {
             H.yp[0].yrec = H.upload(yrec);
         }
         H.yp[0].resident_grid = std::getenv("DFB_Y_PERSIST") ? std::atoi(std::getenv("DFB_Y_PERSIST")) : 0;
+        H.yp[0].tk = ytk;
         H.yp[0].groups = H.upload(groups);
         H.yp[0].tiles = H.upload(tiles);
         H.yp[0].cmat = H.upload(cmat);
@@ -330,7 +343,7 @@ void build_device(dfb_filter_s& H) {
             const FieldDev& F = H.D[b].f[f];
             cuuint64_t dims[2] = {(cuuint64_t)F.We, (cuuint64_t)F.rows_y};
             cuuint64_t strides[1] = {(cuuint64_t)F.pitch_y * sizeof(double)};
-            cuuint32_t box[2] = {(cuuint32_t)Y_TK, (cuuint32_t)RC};
+            cuuint32_t box[2] = {(cuuint32_t)ytk, (cuuint32_t)RC};
             cuuint32_t estr[2] = {1u, 1u};
             CUresult r = encode_tiled()(&H.maps[b].m[f], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, F.r_ys, dims, strides, box, estr,
                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,

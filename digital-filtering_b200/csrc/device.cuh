@@ -104,6 +104,7 @@ struct YParams {
     const double* yrec;        // recursive groups, 16 doubles per half-width N: a, -a^(N+1), 1/s, a^-1 .. a^-7, a^2, a^4, a^8
     int tile0;                 // first tile of this launch in `tiles` (dense tiles first, then recursive tiles)
     int n_tiles;               // tiles of this launch (dense kernel: walked with stride gridDim.x)
+    int tk;                    // columns per dense tile: 128, or 64 for planes that do not fill the GPU (never with recursive tiles)
     int resident_grid;         // > 0: launch the dense kernel with at most this many CTAs (one wave), each walking several tiles
     unsigned long long* prof;  // [8] cycle counters (development probe, filled when debug != 0)
     unsigned long long* tl;    // development aid (DFB_TIMELINE), see NoiseParams

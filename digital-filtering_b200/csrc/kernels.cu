@@ -215,18 +215,20 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
 // and exact zeros outside each row's own half-width, so rows of different N share one pass
 // (adding +0*x leaves a sum unchanged; noise is finite).
 // =================================================================================================
-template <int RC, int NS>
+template <int RC, int NS, int TK = Y_TK>
 struct YSmem {
-    double samples[NS][RC][Y_TK];
+    double samples[NS][RC][TK];
     double coefs[NS][Y_G][RC][YJ];
     uint64_t full[NS];
     uint64_t empty[NS];
 };
 
-template <int RC, int NS>
+// TK = 128 columns per tile (lane owns 4) or 64 (lane owns 2: twice as many, half as heavy CTAs for planes that do not fill the GPU)
+template <int RC, int NS, int TK>
 __global__ void __launch_bounds__(160, 3) ysweep_tma_kernel(const __grid_constant__ YMaps maps, const YParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    YSmem<RC, NS>& sm = *reinterpret_cast<YSmem<RC, NS>*>(smem_raw);
+    YSmem<RC, NS, TK>& sm = *reinterpret_cast<YSmem<RC, NS, TK>*>(smem_raw);
+    constexpr int NC = TK / 32;            // columns per lane
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // One tile per CTA (gridDim.x == n_tiles), or a resident grid whose CTAs walk the (longest-first) tile list with a stride:
     // with every CTA resident from the start, the block scheduler has nothing of this kernel pending and lets the next step's
@@ -262,7 +264,7 @@ __global__ void __launch_bounds__(160, 3) ysweep_tma_kernel(const __grid_constan
             for (int c = t.cbegin; c < t.cend; ++c, ++i) {
                 const int s = i % NS;
                 if (i >= NS) mbar_wait(&sm.empty[s], ((i / NS) - 1) & 1);
-                uint32_t bytes = (uint32_t)(sizeof(double) * RC * Y_TK);
+                uint32_t bytes = (uint32_t)(sizeof(double) * RC * TK);
 #pragma unroll
                 for (int w = 0; w < Y_G; ++w) if (c >= cs[w] && c < ce[w]) bytes += (uint32_t)(sizeof(double) * RC * YJ);
                 mbar_expect_tx(&sm.full[s], bytes);
@@ -280,9 +282,11 @@ __global__ void __launch_bounds__(160, 3) ysweep_tma_kernel(const __grid_constan
     if (have) g = P.groups[t.g0 + warp];
     const int my_cs = have ? g.cstart : 0, my_ce = have ? g.cstart + g.nchunks : 0;
 
-    double acc[YJ][4];
+    double acc[YJ][NC];
 #pragma unroll
-    for (int jj = 0; jj < YJ; ++jj) { acc[jj][0] = acc[jj][1] = acc[jj][2] = acc[jj][3] = 0.0; }
+    for (int jj = 0; jj < YJ; ++jj)
+#pragma unroll
+        for (int q = 0; q < NC; ++q) acc[jj][q] = 0.0;
 
     long long tw = 0, tc = 0;
     const long long tstart = P.debug ? clock64() : 0;
@@ -297,18 +301,29 @@ __global__ void __launch_bounds__(160, 3) ysweep_tma_kernel(const __grid_constan
 #pragma unroll
             for (int r = 0; r < RC; ++r) {
                 const double2 xa = *reinterpret_cast<const double2*>(&sm.samples[s][r][2 * lane]);
-                const double2 xb = *reinterpret_cast<const double2*>(&sm.samples[s][r][64 + 2 * lane]);
+                if (NC == 4) {
+                    const double2 xb = *reinterpret_cast<const double2*>(&sm.samples[s][r][(TK / 2 + 2 * lane) % TK]);
 #pragma unroll
-                for (int jj = 0; jj < YJ; jj += 2) {
-                    const double2 cc = *reinterpret_cast<const double2*>(&sm.coefs[s][warp][r][jj]);
-                    acc[jj][0] = fma(cc.x, xa.x, acc[jj][0]);
-                    acc[jj][1] = fma(cc.x, xa.y, acc[jj][1]);
-                    acc[jj][2] = fma(cc.x, xb.x, acc[jj][2]);
-                    acc[jj][3] = fma(cc.x, xb.y, acc[jj][3]);
-                    acc[jj + 1][0] = fma(cc.y, xa.x, acc[jj + 1][0]);
-                    acc[jj + 1][1] = fma(cc.y, xa.y, acc[jj + 1][1]);
-                    acc[jj + 1][2] = fma(cc.y, xb.x, acc[jj + 1][2]);
-                    acc[jj + 1][3] = fma(cc.y, xb.y, acc[jj + 1][3]);
+                    for (int jj = 0; jj < YJ; jj += 2) {
+                        const double2 cc = *reinterpret_cast<const double2*>(&sm.coefs[s][warp][r][jj]);
+                        acc[jj][0] = fma(cc.x, xa.x, acc[jj][0]);
+                        acc[jj][1] = fma(cc.x, xa.y, acc[jj][1]);
+                        acc[jj][NC - 2] = fma(cc.x, xb.x, acc[jj][NC - 2]);
+                        acc[jj][NC - 1] = fma(cc.x, xb.y, acc[jj][NC - 1]);
+                        acc[jj + 1][0] = fma(cc.y, xa.x, acc[jj + 1][0]);
+                        acc[jj + 1][1] = fma(cc.y, xa.y, acc[jj + 1][1]);
+                        acc[jj + 1][NC - 2] = fma(cc.y, xb.x, acc[jj + 1][NC - 2]);
+                        acc[jj + 1][NC - 1] = fma(cc.y, xb.y, acc[jj + 1][NC - 1]);
+                    }
+                } else {
+#pragma unroll
+                    for (int jj = 0; jj < YJ; jj += 2) {
+                        const double2 cc = *reinterpret_cast<const double2*>(&sm.coefs[s][warp][r][jj]);
+                        acc[jj][0] = fma(cc.x, xa.x, acc[jj][0]);
+                        acc[jj][1] = fma(cc.x, xa.y, acc[jj][1]);
+                        acc[jj + 1][0] = fma(cc.y, xa.x, acc[jj + 1][0]);
+                        acc[jj + 1][1] = fma(cc.y, xa.y, acc[jj + 1][1]);
+                    }
                 }
             }
         }
@@ -327,7 +342,7 @@ __global__ void __launch_bounds__(160, 3) ysweep_tma_kernel(const __grid_constan
         if (jj >= g.nrows) break;
         double* dst = F.r_zs + (size_t)(g.j0 + jj) * F.pitch_z + F.zoff + F.yshift;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < NC / 2; ++h) {
             const int x = xa0 + 64 * h;
             if (vec_ok && x + 1 < F.We) {
                 *reinterpret_cast<double2*>(dst + x) = make_double2(acc[jj][2 * h], acc[jj][2 * h + 1]);
@@ -1090,10 +1105,14 @@ int noise_threads() { return NOISE_THREADS * NOISE_PAIRS; }
 int ysweep_rc() { return Y_RC; }
 
 cudaError_t ysweep_prepare() {
-    cudaError_t e = cudaFuncSetAttribute(ysweep_tma_kernel<Y_RC, Y_NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)sizeof(YSmem<Y_RC, Y_NS>));
+    cudaError_t e = cudaFuncSetAttribute(ysweep_tma_kernel<Y_RC, Y_NS, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(YSmem<Y_RC, Y_NS, 128>));
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(ysweep_tma_kernel<Y_RC, Y_NS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    e = cudaFuncSetAttribute(ysweep_tma_kernel<Y_RC, Y_NS, 128>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(ysweep_tma_kernel<Y_RC, Y_NS, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(YSmem<Y_RC, Y_NS, 64>));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(ysweep_tma_kernel<Y_RC, Y_NS, 64>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(ysweep_rec_kernel<Y_RC, Y_NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(YSmem<Y_RC, Y_NS>));
     if (e != cudaSuccess) return e;
@@ -1116,8 +1135,14 @@ cudaError_t launch_ysweep_tma(const YMaps& maps, const YParams& P, int n_dense, 
         Q.tile0 = 0;
         Q.n_tiles = n_dense;
         const int grid = P.resident_grid > 0 ? (n_dense < P.resident_grid ? n_dense : P.resident_grid) : n_dense;
-        cudaLaunchConfig_t cfg = pdl_config((unsigned)grid, 160, sizeof(YSmem<Y_RC, Y_NS>), st, &attr);
-        cudaError_t e = cudaLaunchKernelEx(&cfg, ysweep_tma_kernel<Y_RC, Y_NS>, maps, Q);
+        cudaError_t e;
+        if (P.tk == 64) {
+            cudaLaunchConfig_t cfg = pdl_config((unsigned)grid, 160, sizeof(YSmem<Y_RC, Y_NS, 64>), st, &attr);
+            e = cudaLaunchKernelEx(&cfg, ysweep_tma_kernel<Y_RC, Y_NS, 64>, maps, Q);
+        } else {
+            cudaLaunchConfig_t cfg = pdl_config((unsigned)grid, 160, sizeof(YSmem<Y_RC, Y_NS, 128>), st, &attr);
+            e = cudaLaunchKernelEx(&cfg, ysweep_tma_kernel<Y_RC, Y_NS, 128>, maps, Q);
+        }
         if (e != cudaSuccess) return e;
     }
     if (n_rec > 0) {
