@@ -80,14 +80,16 @@ __device__ __forceinline__ void normal_pair(uint64_t state, uint64_t inc, double
 #pragma unroll
     for (int k = DFB_COS_NC - 2; k >= 0; --k) Cc = __fma_rn(Cc, x2, c_cos[k]);
     double cx = __fma_rn(x2, Cc, 1.0);
-    if (oct & 1u) { double tmp = sx; sx = cx; cx = tmp; }
-    double sn, cs;
-    switch (oct >> 1) {
-        case 0:  sn =  sx; cs =  cx; break;
-        case 1:  sn =  cx; cs = -sx; break;
-        case 2:  sn = -sx; cs = -cx; break;
-        default: sn = -cx; cs =  sx; break;
-    }
+    // octant -> (sin, cos) of the full angle without data-dependent branches (lanes of a warp sit in all eight octants):
+    //   odd octant: swap;  quadrant q = oct >> 1:  q odd: (sn, cs) = (c, -s) else (s, c);  q >= 2: negate both.
+    // Negation = sign-bit flip, the same value the host's unary minus produces.
+    const bool swap_sc = ((oct ^ (oct >> 1)) & 1u) != 0;      // (oct & 1) swaps once, (q & 1) swaps again
+    double sn = swap_sc ? cx : sx, cs = swap_sc ? sx : cx;
+    const unsigned q = oct >> 1;
+    const long long neg_sn = (long long)(q >> 1) << 63;                       // q = 2, 3
+    const long long neg_cs = (long long)(((q + 1u) >> 1) & 1u) << 63;         // q = 1, 2
+    sn = __longlong_as_double(__double_as_longlong(sn) ^ neg_sn);
+    cs = __longlong_as_double(__double_as_longlong(cs) ^ neg_cs);
     z0 = __dmul_rn(r, cs);
     z1 = __dmul_rn(r, sn);
 }
