@@ -87,6 +87,41 @@ class SlabFilter:
                 req.wait()
         return bufs
 
+    def gather_async(self, fields, torch, device):
+        """The same gather, overlapped with the NEXT step: the fields are staged (device-to-device) on a communication stream as
+        soon as the handle's stream has finished the step, the handle's stream only waits for that staging copy, and the NCCL
+        transfer of the staged copy runs while the next filter(dt) computes.  Returns a ticket for gather_wait()."""
+        hs = torch.cuda.ExternalStream(self.filt.stream(), device=device)
+        if not hasattr(self, "_comm"):
+            self._comm = torch.cuda.Stream(device=device)
+        done = torch.cuda.Event()
+        done.record(hs)                                              # step t is complete on the handle's stream
+        with torch.cuda.stream(self._comm):
+            self._comm.wait_event(done)
+            mine = torch.stack([self.filt.device_tensor(w) for w in fields])      # staged copy [F, Ny, W]
+            staged = torch.cuda.Event()
+            staged.record(self._comm)
+            bufs, ops = None, []
+            if self.rank == self.dst:
+                bufs = [torch.empty((len(fields), self.Ny, k1 - k0), dtype=mine.dtype, device=device) for k0, k1 in self.bounds]
+                bufs[self.dst].copy_(mine)
+                for r in range(self.world):
+                    if r != self.dst:
+                        ops.append(self.dist.P2POp(self.dist.irecv, bufs[r], r))
+            else:
+                ops.append(self.dist.P2POp(self.dist.isend, mine, self.dst))
+            reqs = self.dist.batch_isend_irecv(ops) if ops else []
+        hs.wait_event(staged)                                        # step t+1 may overwrite the fields once they are staged
+        return dict(reqs=reqs, bufs=bufs, keep=mine)
+
+    def gather_wait(self, ticket, torch):
+        """Completes a gather_async: the communication stream (and the caller's current stream) wait for the transfer."""
+        with torch.cuda.stream(self._comm):
+            for req in ticket["reqs"]:
+                req.wait()
+        torch.cuda.current_stream().wait_stream(self._comm)
+        return ticket["bufs"]
+
     def plane_on_dst(self, bufs, field_index):
         """(Ny, Nz) numpy plane of one gathered field (dst rank only)."""
         return assemble_plane([b[field_index].cpu().numpy() for b in bufs], self.bounds, self.Ny, self.NzG)

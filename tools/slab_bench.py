@@ -77,12 +77,48 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()) / args.steps
 
+    def timed_overlapped():
+        """filter(t+1) runs while the gather of step t is on the wire (SlabFilter.gather_async)"""
+        prev = None
+        for _ in range(3):
+            sf.filter(1e-7)
+            tk = sf.gather_async(FIELDS, torch, dev)
+            if prev is not None:
+                sf.gather_wait(prev, torch)
+            prev = tk
+        sf.gather_wait(prev, torch)
+        sf.filt.sync(); dist.barrier(); torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(torch.cuda.current_stream())
+        prev = None
+        for _ in range(args.steps):
+            sf.filter(1e-7)
+            tk = sf.gather_async(FIELDS, torch, dev)
+            if prev is not None:
+                sf.gather_wait(prev, torch)
+            prev = tk
+        last = sf.gather_wait(prev, torch)
+        torch.cuda.current_stream().wait_stream(stream)
+        b.record(torch.cuda.current_stream())
+        sf.filt.sync(); torch.cuda.synchronize(); dist.barrier()
+        t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / args.steps, last
+
     ms_nogather = timed(False)
     ms_gather = timed(True)
+    ms_overlap, last = timed_overlapped()
+    # the overlapped gather must deliver the same plane as the synchronous one (same step count on every rank)
+    sf.filt.sync()
+    ref_bufs = sf.gather(FIELDS, torch, dev)
+    ok_overlap = True
+    if rank == 0:
+        ok_overlap = all(bool(torch.equal(x, y)) for x, y in zip(last, ref_bufs))
     if rank == 0:
         cells = plane["Ny"] * plane["Nz"]
         print(json.dumps(dict(workload=plane["name"], n_gpus=world, slab_equals_whole_plane=bool(ok), slabs=sf.bounds,
-                              ms_per_step_no_gather=ms_nogather, ms_per_step_with_gather=ms_gather,
+                              ms_per_step_no_gather=ms_nogather, ms_per_step_with_gather=ms_gather, ms_per_step_with_gather_overlapped=ms_overlap,
+                              overlapped_gather_equals_synchronous=bool(ok_overlap),
                               cell_updates_per_s_no_gather=cells / (ms_nogather * 1e-3), cell_updates_per_s_with_gather=cells / (ms_gather * 1e-3),
                               gathered_bytes_per_step=40 * cells * (world - 1) // world)), flush=True)
     sf.filt.close()
