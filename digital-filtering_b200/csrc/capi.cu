@@ -205,29 +205,50 @@ void build_device(dfb_filter_s& H) {
         // equal N: whole groups of YJ rows out of a run, a tail of >= 4 rows as a short group, shorter leftovers merged into a
         // mixed (dense) group with their neighbours.  DFB_Y_MODE=0: fixed groups of YJ rows, all dense.
         constexpr int Y_REC_MIN_N = 16;
-        // The recursive form streams the same windows as the dense one but does ~6x less arithmetic on them, so it runs at the
-        // L2 -> SM streaming rate; it wins where (nearly) all of the y work sits in long runs of one N >= 16 (uniform planes:
-        // 0.223 -> 0.166 ms/step at 1024x2048, N = 128) and loses on boundary-layer grids whose N_y changes every few rows
-        // (0.143 -> 0.166: more, shorter groups, each with its whole window).  Default: on when >= 90 % of the y taps lie in runs
-        // of >= 16 equal half-widths >= 16; DFB_Y_MODE=1 / 0 forces it on / off.
+        // Recursive row groups (ysweep_rec_kernel) or not?  A group can only be recursive if all its rows share one N >= 16, so the
+        // groups then follow the runs of equal N_y: more, shorter groups, each streaming its whole window.  Cost model in units of
+        // 8-row chunks x columns: a dense chunk costs 256 FMAs per lane, a bulk chunk of a recursive group 32.  Measured: uniform
+        // planes 0.223 -> 0.159 ms/step (model ratio 0.20), 4096x8192 boundary-layer profile 2.13 -> 2.05 (0.54), 1024x2048
+        // boundary-layer profile 0.142 -> 0.153 (0.67: N_y changes every ~9 rows where it is large).  On when the ratio is below 0.6;
+        // DFB_Y_MODE=1 / 0 forces it on / off.
         bool yrec_on;
         {
-            double taps_all = 0, taps_long = 0;
+            double dense = 0, hybrid = 0;
             for (int f = 0; f < 3; ++f) {
                 const std::vector<int>& Nr = P.f[f].N_y_row;
+                const int Nmx = P.f[f].Ny_max;
+                auto chunks = [&](int j0, int nr, int N) { return (j0 + nr - 1 + Nmx + N) / RC - (j0 + Nmx - N) / RC + 1; };
+                for (int j0 = 0; j0 < Ny; j0 += YJ) {
+                    const int nr = std::min(YJ, Ny - j0);
+                    int N = 0;
+                    for (int jj = 0; jj < nr; ++jj) N = std::max(N, Nr[j0 + jj]);
+                    dense += 256.0 * chunks(j0, nr, N);
+                }
                 for (int j = 0; j < Ny;) {
-                    int r = 1;
-                    while (j + r < Ny && Nr[j + r] == Nr[j]) ++r;
-                    const double w = (double)r * (2.0 * Nr[j] + 1.0);
-                    taps_all += w;
-                    if (r >= 16 && Nr[j] >= Y_REC_MIN_N) taps_long += w;
-                    j += r;
+                    int R = 1;
+                    while (j + R < Ny && Nr[j + R] == Nr[j]) ++R;
+                    const int N = Nr[j];
+                    if (N >= Y_REC_MIN_N && R >= 4) {
+                        const int nr = std::min(R, YJ), w0 = j + Nmx - N;
+                        int nbulk = 0;
+                        for (int c = w0 / RC; c <= (w0 + 2 * N + nr - 1) / RC; ++c) {
+                            const int i0 = c * RC - w0;
+                            if ((i0 >= nr - 1 && i0 + RC - 1 <= N - 1) || (i0 >= N + nr && i0 + RC - 1 <= 2 * N)) ++nbulk;
+                        }
+                        hybrid += 256.0 * (chunks(j, nr, N) - nbulk) + 32.0 * nbulk;
+                        j += nr;
+                    } else {
+                        const int nr = std::min(std::min(R, YJ), Ny - j);          // (mixed groups merge leftovers: close enough)
+                        hybrid += 256.0 * chunks(j, nr, N) * (R < 4 ? 0.5 : 1.0);
+                        j += nr;
+                    }
                 }
             }
-            yrec_on = taps_long >= 0.9 * taps_all;
+            yrec_on = hybrid < 0.6 * dense;
             if (const char* ym = std::getenv("DFB_Y_MODE")) yrec_on = std::atoi(ym) != 0;
         }
         std::vector<char> yrec_need(P.coef.Nmax + 1, 0);
+        std::vector<double> ygc;              // recursive groups: 8 low-bulk + 8 high-bulk factors each
         std::vector<YTile> tiles_dense, tiles_rec;
         // columns per dense tile: 64 instead of 128 when 128-column tiles would not even give every SM two CTAs (the reference's
         // default plane: 192 tiles of up to 57 chunks; y-sweep 0.036 -> 0.026 ms); recursive tiles always take 128
@@ -268,12 +289,10 @@ void build_device(dfb_filter_s& H) {
                 g.nchunks = hi / RC + 1 - g.cstart;
                 g.rec = uniform ? 1 : 0;
                 g.w0 = lo;
-                if (g.rec) {
-                    g.cmat_off = -1;
-                    yrec_need[g.Nmax] = 1;
-                } else {
-                    g.cmat_off = (long long)cmat.size();
-                    cmat.resize(cmat.size() + (size_t)g.nchunks * RC * YJ, 0.0);
+                // band matrix of the group (recursive groups only use the chunks at the ends of the window and around the output rows)
+                g.cmat_off = (long long)cmat.size();
+                cmat.resize(cmat.size() + (size_t)g.nchunks * RC * YJ, 0.0);
+                {
                     double* cm = cmat.data() + g.cmat_off;
                     for (int jj = 0; jj < g.nrows; ++jj) {
                         const int N = FP.N_y_row[j0 + jj];
@@ -281,6 +300,30 @@ void build_device(dfb_filter_s& H) {
                         for (int i = -N; i <= N; ++i)
                             cm[(size_t)(j0 + jj + FP.Ny_max + i - g.cstart * RC) * YJ + jj] = b[i];
                     }
+                }
+                if (g.rec) {
+                    // Bulk chunks: all 8 rows lie in EVERY output row's window and on one side of every centre, so their contribution
+                    // to output t is one shared geometric sum times a per-row factor (<= 1):
+                    //   low  bulk (window positions nrows-1 <= i <= N-1):  out_t += s^-1 a^(N+t-i_ll) * G,  G = sum a^(i_ll-i) x_i
+                    //   high bulk (N+nrows <= i <= 2N):                    out_t += s^-1 a^(i_fh-N-t) * K,  K = sum a^(i-i_fh) x_i
+                    // (i_ll / i_fh: last row of the last low / first row of the first high bulk chunk).  16 factors per group.
+                    const int N = g.Nmax;
+                    int i_ll = -1, i_fh = -1;
+                    for (int c = g.cstart; c < g.cstart + g.nchunks; ++c) {
+                        const int i0 = c * RC - g.w0;
+                        if (i0 >= g.nrows - 1 && i0 + RC - 1 <= N - 1) i_ll = i0 + RC - 1;
+                        if (i_fh < 0 && i0 >= N + g.nrows && i0 + RC - 1 <= 2 * N) i_fh = i0;
+                    }
+                    const long double a = (long double)std::exp(-2.0 * 3.14159265358979323846 * 1.0 / N);
+                    const long double cn = (long double)*P.coef.centre(N);
+                    g.gc_off = (int)(ygc.size() / 16);
+                    ygc.resize(ygc.size() + 16, 0.0);
+                    double* q = ygc.data() + (size_t)g.gc_off * 16;
+                    for (int t = 0; t < g.nrows; ++t) {
+                        q[t] = i_ll >= 0 ? (double)(cn * std::pow(a, (long double)(N + t - i_ll))) : 0.0;
+                        q[8 + t] = i_fh >= 0 ? (double)(cn * std::pow(a, (long double)(i_fh - N - t))) : 0.0;
+                    }
+                    yrec_need[N] = 1;
                 }
                 gk[g.rec].push_back(g);
                 j0 += nr;
@@ -325,6 +368,7 @@ void build_device(dfb_filter_s& H) {
                 q[10] = (double)(a * a); q[11] = (double)std::pow(a, 4.0L); q[12] = (double)std::pow(a, 8.0L);
             }
             H.yp[0].yrec = H.upload(yrec);
+            H.yp[0].ygc = H.upload(ygc);
         }
         H.yp[0].resident_grid = std::getenv("DFB_Y_PERSIST") ? std::atoi(std::getenv("DFB_Y_PERSIST")) : 0;
         H.yp[0].tk = ytk;

@@ -57,9 +57,10 @@ struct YGroup {                // YJ consecutive output rows of one field
     int field, j0, nrows, Nmax;
     int cstart;                // first chunk of the window on the field's absolute chunk grid (chunk c = padded rows [c*RC, (c+1)*RC))
     int nchunks;               // chunks the window touches
-    long long cmat_off;        // doubles, into the band-matrix pool: Cmat[(row - cstart*RC)][YJ]; -1: recursive group (no matrix)
+    long long cmat_off;        // doubles, into the band-matrix pool: Cmat[(row - cstart*RC)][YJ]
     int rec;                   // 1: every row has the same half-width N = Nmax >= 16: recursive evaluation (ysweep_rec_kernel)
     int w0;                    // padded row of the group's first window sample (= j0 + Ny_max - Nmax)
+    int gc_off;                // recursive: index (x16 doubles) of the group's bulk factors in YParams::ygc
 };
 struct YTile {                 // up to Y_G consecutive groups x Y_TK columns
     int field, col0, g0, ngroups;
@@ -101,7 +102,8 @@ struct YParams {
     const YTile* tiles;
     const double* cmat;
     int* zcounter;             // work counter of the z-sweep that follows (reset here)
-    const double* yrec;        // recursive groups, 16 doubles per half-width N: a, -a^(N+1), 1/s, a^-1 .. a^-7, a^2, a^4, a^8
+    const double* yrec;        // recursive groups, 16 doubles per half-width N: a at [0], a^2, a^4, a^8 at [10..12]
+    const double* ygc;         // recursive groups, 16 doubles each: factors of the low-bulk sum [0..7] and of the high-bulk sum [8..15] per output row
     int tile0;                 // first tile of this launch in `tiles` (dense tiles first, then recursive tiles)
     int n_tiles;               // tiles of this launch (dense kernel: walked with stride gridDim.x)
     int tk;                    // columns per dense tile: 128, or 64 for planes that do not fill the GPU (never with recursive tiles)

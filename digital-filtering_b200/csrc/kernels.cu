@@ -372,16 +372,16 @@ __global__ void __launch_bounds__(160, 3) ysweep_tma_kernel(const __grid_constan
 // H2y tuned, recursive form: row groups whose rows all share one half-width N >= 16.
 //
 // The reference's coefficients are a truncated two-sided exponential, b_i = a^|i| / s with a = exp(-2 pi / N)
-// (df.cpp:168-177).  Rows stream by in ascending order exactly as in ysweep_tma_kernel (same tiles, same TMA ring, no band
-// matrices); with i = position in the group's window (padded row w0 is i = 0, the group's first output row is i = N):
-//   causal      G <- a G + x over i = 0 .. N+nrows-1;   F_t = G(i = N+t) - a^(N+1) G(i = t-1)      (the correction is the sum
-//               of the window's first t samples, i.e. G itself after t rows: a snapshot, no extra work)
-//   anti-causal K <- K + a^(i-N) x over i >= N;          B_t = a^-t (K(i = 2N+t) - K(i = N+t-1))
-//   out_t = (F_t + B_t - x_t) / s,  t = 0 .. nrows-1.
-// Whole chunks of 8 rows that contain no row of special meaning fold their 8 samples in a binary tree (a, a^2, a^4) and touch
-// the running sums once: 8 FMAs per column and chunk instead of 64.  a^-t <= a^-7 <= 15.6 for N >= 16 bounds the cancellation
-// in B_t; measured against the oracle: <= 1e-14 of the rms (gate 1e-12).  Every operation is an explicit round-to-nearest
-// intrinsic; a column's result does not depend on the slab it is computed in.
+// (df.cpp:168-177).  Most rows of a group's window lie in EVERY output row's window and on one side of every output row:
+// with i = position in the window (padded row w0 is i = 0, output row t is centred on i = N + t)
+//   low  bulk, nrows-1 <= i <= N-1:   its weight for output t is a^(N+t-i) = a^(N+t-i_ll) * a^(i_ll-i)
+//   high bulk, N+nrows <= i <= 2N:    its weight for output t is a^(i-N-t) = a^(i_fh-N-t) * a^(i-i_fh)
+// so whole 8-row chunks of bulk rows are folded in a binary tree (a, a^2, a^4) into ONE running sum per column,
+// G <- a^8 G + T or K <- K + p T, p <- a^8 p (8 FMAs per column and chunk instead of 64), and at the end
+// out_t = dense_t + gl_t G + gh_t K with 16 host-computed factors per group, all <= 1 (no cancellation).  The chunks at the two ends
+// of the window and around the output rows go through the dense band-matrix path exactly as in ysweep_tma_kernel.
+// Same tiles, same TMA ring, same barriers; band-matrix slices are only fetched for the dense chunks.
+// Measured against the oracle: <= 1e-14 of the rms (gate 1e-12).  A column's result does not depend on the slab it is computed in.
 // =================================================================================================
 template <int RC, int NS>
 __global__ void __launch_bounds__(160, 3) ysweep_rec_kernel(const __grid_constant__ YMaps maps, const YParams P) {
@@ -401,15 +401,43 @@ __global__ void __launch_bounds__(160, 3) ysweep_rec_kernel(const __grid_constan
     __syncthreads();
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
-    if (warp == Y_G) {                     // producer: the union window, sample chunks only
+    // chunk c of a group: 1 = low bulk, 2 = high bulk, 0 = dense (band matrix)
+    auto chunk_kind = [](int c, int w0, int Nn, int nrows) {
+        const int i0 = c * RC - w0;
+        if (i0 >= nrows - 1 && i0 + RC - 1 <= Nn - 1) return 1;
+        if (i0 >= Nn + nrows && i0 + RC - 1 <= 2 * Nn) return 2;
+        return 0;
+    };
+
+    if (warp == Y_G) {                     // producer
         if (lane == 0) {
             const CUtensorMap* map = &maps.m[t.field];
+            int cs[Y_G], ce[Y_G], gw0[Y_G], gN[Y_G], gnr[Y_G];
+            const double* cm[Y_G];
+#pragma unroll
+            for (int w = 0; w < Y_G; ++w) {
+                if (w < t.ngroups) {
+                    const YGroup g = P.groups[t.g0 + w];
+                    cs[w] = g.cstart; ce[w] = g.cstart + g.nchunks; cm[w] = P.cmat + g.cmat_off; gw0[w] = g.w0; gN[w] = g.Nmax; gnr[w] = g.nrows;
+                } else { cs[w] = 0; ce[w] = 0; cm[w] = nullptr; gw0[w] = 0; gN[w] = 0; gnr[w] = 0; }
+            }
             int i = 0;
             for (int c = t.cbegin; c < t.cend; ++c, ++i) {
                 const int s = i % NS;
                 if (i >= NS) mbar_wait(&sm.empty[s], ((i / NS) - 1) & 1);
-                mbar_expect_tx(&sm.full[s], (uint32_t)(sizeof(double) * RC * Y_TK));
+                bool need[Y_G];
+                uint32_t bytes = (uint32_t)(sizeof(double) * RC * Y_TK);
+#pragma unroll
+                for (int w = 0; w < Y_G; ++w) {
+                    need[w] = c >= cs[w] && c < ce[w] && chunk_kind(c, gw0[w], gN[w], gnr[w]) == 0;
+                    if (need[w]) bytes += (uint32_t)(sizeof(double) * RC * YJ);
+                }
+                mbar_expect_tx(&sm.full[s], bytes);
                 tma_load_2d(&sm.samples[s][0][0], map, t.col0, c * RC, &sm.full[s]);
+#pragma unroll
+                for (int w = 0; w < Y_G; ++w)
+                    if (need[w])
+                        tma_load_1d(&sm.coefs[s][w][0][0], cm[w] + (long long)(c - cs[w]) * RC * YJ, RC * YJ * sizeof(double), &sm.full[s]);
             }
         }
         return;
@@ -419,10 +447,10 @@ __global__ void __launch_bounds__(160, 3) ysweep_rec_kernel(const __grid_constan
     YGroup g{};
     if (have) g = P.groups[t.g0 + warp];
     const int my_cs = have ? g.cstart : 0, my_ce = have ? g.cstart + g.nchunks : 0;
-    const int Nn = g.Nmax, nrows = g.nrows, i_last = 2 * g.Nmax + g.nrows - 1;
+    const int Nn = g.Nmax, nrows = g.nrows;
     const double* par = P.yrec + (size_t)Nn * 16;
-    double ra = 0.0, rnaN1 = 0.0, rcn = 0.0, a2 = 0.0, a4 = 0.0, a8 = 0.0;
-    if (have) { ra = __ldg(par); rnaN1 = __ldg(par + 1); rcn = __ldg(par + 2); a2 = __ldg(par + 10); a4 = __ldg(par + 11); a8 = __ldg(par + 12); }
+    double ra = 0.0, a2 = 0.0, a4 = 0.0, a8 = 0.0;
+    if (have) { ra = __ldg(par); a2 = __ldg(par + 10); a4 = __ldg(par + 11); a8 = __ldg(par + 12); }
 
     double acc[YJ][4];
 #pragma unroll
@@ -434,9 +462,9 @@ __global__ void __launch_bounds__(160, 3) ysweep_rec_kernel(const __grid_constan
         const int s = it % NS;
         mbar_wait(&sm.full[s], (it / NS) & 1);
         if (c >= my_cs && c < my_ce) {
-            const int i0 = c * RC - g.w0;                       // window position of the chunk's first row
-            if (i0 >= nrows - 1 && i0 + RC - 1 < Nn) {
-                // ---- all 8 rows only feed G ----
+            const int kind = chunk_kind(c, g.w0, Nn, nrows);
+            if (kind == 1) {
+                // ---- low bulk: G <- a^8 G + sum_r a^(7-r) x_r ----
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     double2 x[RC];
@@ -450,8 +478,8 @@ __global__ void __launch_bounds__(160, 3) ysweep_rec_kernel(const __grid_constan
                     G[2 * h] = __fma_rn(a8, G[2 * h], x[0].x);
                     G[2 * h + 1] = __fma_rn(a8, G[2 * h + 1], x[0].y);
                 }
-            } else if (i0 >= Nn + nrows && i0 + RC - 1 < 2 * Nn) {
-                // ---- all 8 rows only feed K: K += pw * sum_r a^r x_r ----
+            } else if (kind == 2) {
+                // ---- high bulk: K += p * sum_r a^r x_r, p <- a^8 p ----
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     double2 x[RC];
@@ -467,51 +495,22 @@ __global__ void __launch_bounds__(160, 3) ysweep_rec_kernel(const __grid_constan
                 }
                 pw = __dmul_rn(pw, a8);
             } else {
-                // ---- chunks with the window's ends, a snapshot row, an output row or a closing row: row by row.  The output row
-                // index is a run-time value: compare-and-select over the 8 accumulator rows keeps them in registers (indexing
-                // them dynamically puts them in local memory: measured slower)
-#pragma unroll 1
+                // ---- window ends and the chunks around the output rows: dense band matrix, as in ysweep_tma_kernel ----
+#pragma unroll
                 for (int r = 0; r < RC; ++r) {
-                    const int i = i0 + r;
-                    if (i < 0 || i > i_last) continue;
                     const double2 xa = *reinterpret_cast<const double2*>(&sm.samples[s][r][2 * lane]);
                     const double2 xb = *reinterpret_cast<const double2*>(&sm.samples[s][r][64 + 2 * lane]);
-                    const double x[4] = {xa.x, xa.y, xb.x, xb.y};
-                    if (i <= Nn + nrows - 1) {
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) G[q] = __fma_rn(ra, G[q], x[q]);
-                    }
-                    const int ts = i + 1, to = i - Nn, te = i - 2 * Nn;   // snapshot for row ts / output row to / closing row te
-                    if (ts <= nrows - 1) {
-#pragma unroll
-                        for (int tt = 1; tt < YJ; ++tt)
-                            if (tt == ts) {
-#pragma unroll
-                                for (int q = 0; q < 4; ++q) acc[tt][q] = __dmul_rn(rnaN1, G[q]);
-                            }
-                    }
-                    if (to >= 0 && to <= nrows - 1) {
-                        const double ai = to ? __ldg(par + 2 + to) : 0.0;
-#pragma unroll
-                        for (int tt = 0; tt < YJ; ++tt)
-                            if (tt == to) {
-#pragma unroll
-                                for (int q = 0; q < 4; ++q) acc[tt][q] = __dadd_rn(__fma_rn(-ai, K[q], acc[tt][q]), __dsub_rn(G[q], x[q]));
-                            }
-                    }
-                    if (i >= Nn) {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) K[q] = __fma_rn(pw, x[q], K[q]);
-                        pw = __dmul_rn(pw, ra);
-                    }
-                    if (te >= 0) {
-                        const double ai = te ? __ldg(par + 2 + te) : 1.0;
-#pragma unroll
-                        for (int tt = 0; tt < YJ; ++tt)
-                            if (tt == te) {
-#pragma unroll
-                                for (int q = 0; q < 4; ++q) acc[tt][q] = __fma_rn(ai, K[q], acc[tt][q]);
-                            }
+                    for (int jj = 0; jj < YJ; jj += 2) {
+                        const double2 cc = *reinterpret_cast<const double2*>(&sm.coefs[s][warp][r][jj]);
+                        acc[jj][0] = __fma_rn(cc.x, xa.x, acc[jj][0]);
+                        acc[jj][1] = __fma_rn(cc.x, xa.y, acc[jj][1]);
+                        acc[jj][2] = __fma_rn(cc.x, xb.x, acc[jj][2]);
+                        acc[jj][3] = __fma_rn(cc.x, xb.y, acc[jj][3]);
+                        acc[jj + 1][0] = __fma_rn(cc.y, xa.x, acc[jj + 1][0]);
+                        acc[jj + 1][1] = __fma_rn(cc.y, xa.y, acc[jj + 1][1]);
+                        acc[jj + 1][2] = __fma_rn(cc.y, xb.x, acc[jj + 1][2]);
+                        acc[jj + 1][3] = __fma_rn(cc.y, xb.y, acc[jj + 1][3]);
                     }
                 }
             }
@@ -521,16 +520,20 @@ __global__ void __launch_bounds__(160, 3) ysweep_rec_kernel(const __grid_constan
     }
     if (!have) return;
 
+    // out_t = dense_t + gl_t G + gh_t K; then r_zs interior (df.cpp:377): extended column x -> logical column x + yshift
+    const double* gc = P.ygc + (size_t)g.gc_off * 16;
     const int xa0 = t.col0 + 2 * lane;
     const bool vec_ok = ((F.zoff + F.yshift) & 1) == 0;
 #pragma unroll
     for (int jj = 0; jj < YJ; ++jj) {
         if (jj >= g.nrows) break;
+        const double gl = __ldg(gc + jj), gh = __ldg(gc + 8 + jj);
         double* dst = F.r_zs + (size_t)(g.j0 + jj) * F.pitch_z + F.zoff + F.yshift;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int x = xa0 + 64 * h;
-            const double v0 = __dmul_rn(rcn, acc[jj][2 * h]), v1 = __dmul_rn(rcn, acc[jj][2 * h + 1]);
+            const double v0 = __fma_rn(gh, K[2 * h], __fma_rn(gl, G[2 * h], acc[jj][2 * h]));
+            const double v1 = __fma_rn(gh, K[2 * h + 1], __fma_rn(gl, G[2 * h + 1], acc[jj][2 * h + 1]));
             if (vec_ok && x + 1 < F.We) {
                 *reinterpret_cast<double2*>(dst + x) = make_double2(v0, v1);
             } else {
