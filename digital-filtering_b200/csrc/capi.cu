@@ -248,7 +248,7 @@ void build_device(dfb_filter_s& H) {
             if (const char* ym = std::getenv("DFB_Y_MODE")) yrec_on = std::atoi(ym) != 0;
         }
         std::vector<char> yrec_need(P.coef.Nmax + 1, 0);
-        std::vector<double> ygc;              // recursive groups: 8 low-bulk + 8 high-bulk factors each
+        std::vector<double> ygc(16, 0.0);     // recursive groups: 8 low-bulk + 8 high-bulk factors each; entry 0 = zeros (mixed groups)
         std::vector<YTile> tiles_dense, tiles_rec;
         // columns per dense tile: 64 instead of 128 when 128-column tiles would not even give every SM two CTAs (the reference's
         // default plane: 192 tiles of up to 57 chunks; y-sweep 0.036 -> 0.026 ms); recursive tiles always take 128
@@ -328,11 +328,16 @@ void build_device(dfb_filter_s& H) {
                 gk[g.rec].push_back(g);
                 j0 += nr;
             }
-            // tiles: up to Y_G groups of the same kind, neighbours in row order (not necessarily adjacent rows), share one sample stream
-            for (int kind = 0; kind < 2; ++kind) {
+            // tiles: up to Y_G ADJACENT groups share one sample stream.  With recursive groups in play every tile goes through
+            // ysweep_rec_kernel, which runs mixed groups entirely through its dense path (tiles of one kind only, built from
+            // non-adjacent groups and launched as two kernels, measured slower: longer union windows, two tails)
+            {
                 const int first_group = (int)groups.size();
-                groups.insert(groups.end(), gk[kind].begin(), gk[kind].end());
-                const int ng = (int)gk[kind].size();
+                std::vector<YGroup> all = gk[0];
+                all.insert(all.end(), gk[1].begin(), gk[1].end());
+                std::stable_sort(all.begin(), all.end(), [](const YGroup& a, const YGroup& b) { return a.j0 < b.j0; });
+                groups.insert(groups.end(), all.begin(), all.end());
+                const int ng = (int)all.size();
                 for (int gb = 0; gb < ng; gb += Y_G) {
                     YTile t{};
                     t.field = f; t.g0 = first_group + gb; t.ngroups = std::min(Y_G, ng - gb);
@@ -342,8 +347,8 @@ void build_device(dfb_filter_s& H) {
                         t.cbegin = std::min(t.cbegin, g.cstart);
                         t.cend = std::max(t.cend, g.cstart + g.nchunks);
                     }
-                    const int step = kind ? Y_TK : ytk;
-                    for (int c0 = 0; c0 < D.f[f].We; c0 += step) { t.col0 = c0; (kind ? tiles_rec : tiles_dense).push_back(t); }
+                    const int step = yrec_on ? Y_TK : ytk;
+                    for (int c0 = 0; c0 < D.f[f].We; c0 += step) { t.col0 = c0; (yrec_on ? tiles_rec : tiles_dense).push_back(t); }
                 }
             }
         }

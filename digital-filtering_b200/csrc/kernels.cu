@@ -402,7 +402,8 @@ __global__ void __launch_bounds__(160, 3) ysweep_rec_kernel(const __grid_constan
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
     // chunk c of a group: 1 = low bulk, 2 = high bulk, 0 = dense (band matrix)
-    auto chunk_kind = [](int c, int w0, int Nn, int nrows) {
+    auto chunk_kind = [](int rec, int c, int w0, int Nn, int nrows) {
+        if (!rec) return 0;                 // mixed group: dense throughout
         const int i0 = c * RC - w0;
         if (i0 >= nrows - 1 && i0 + RC - 1 <= Nn - 1) return 1;
         if (i0 >= Nn + nrows && i0 + RC - 1 <= 2 * Nn) return 2;
@@ -412,14 +413,14 @@ __global__ void __launch_bounds__(160, 3) ysweep_rec_kernel(const __grid_constan
     if (warp == Y_G) {                     // producer
         if (lane == 0) {
             const CUtensorMap* map = &maps.m[t.field];
-            int cs[Y_G], ce[Y_G], gw0[Y_G], gN[Y_G], gnr[Y_G];
+            int cs[Y_G], ce[Y_G], gw0[Y_G], gN[Y_G], gnr[Y_G], grec[Y_G];
             const double* cm[Y_G];
 #pragma unroll
             for (int w = 0; w < Y_G; ++w) {
                 if (w < t.ngroups) {
                     const YGroup g = P.groups[t.g0 + w];
-                    cs[w] = g.cstart; ce[w] = g.cstart + g.nchunks; cm[w] = P.cmat + g.cmat_off; gw0[w] = g.w0; gN[w] = g.Nmax; gnr[w] = g.nrows;
-                } else { cs[w] = 0; ce[w] = 0; cm[w] = nullptr; gw0[w] = 0; gN[w] = 0; gnr[w] = 0; }
+                    cs[w] = g.cstart; ce[w] = g.cstart + g.nchunks; cm[w] = P.cmat + g.cmat_off; gw0[w] = g.w0; gN[w] = g.Nmax; gnr[w] = g.nrows; grec[w] = g.rec;
+                } else { cs[w] = 0; ce[w] = 0; cm[w] = nullptr; gw0[w] = 0; gN[w] = 0; gnr[w] = 0; grec[w] = 0; }
             }
             int i = 0;
             for (int c = t.cbegin; c < t.cend; ++c, ++i) {
@@ -429,7 +430,7 @@ __global__ void __launch_bounds__(160, 3) ysweep_rec_kernel(const __grid_constan
                 uint32_t bytes = (uint32_t)(sizeof(double) * RC * Y_TK);
 #pragma unroll
                 for (int w = 0; w < Y_G; ++w) {
-                    need[w] = c >= cs[w] && c < ce[w] && chunk_kind(c, gw0[w], gN[w], gnr[w]) == 0;
+                    need[w] = c >= cs[w] && c < ce[w] && chunk_kind(grec[w], c, gw0[w], gN[w], gnr[w]) == 0;
                     if (need[w]) bytes += (uint32_t)(sizeof(double) * RC * YJ);
                 }
                 mbar_expect_tx(&sm.full[s], bytes);
@@ -450,7 +451,7 @@ __global__ void __launch_bounds__(160, 3) ysweep_rec_kernel(const __grid_constan
     const int Nn = g.Nmax, nrows = g.nrows;
     const double* par = P.yrec + (size_t)Nn * 16;
     double ra = 0.0, a2 = 0.0, a4 = 0.0, a8 = 0.0;
-    if (have) { ra = __ldg(par); a2 = __ldg(par + 10); a4 = __ldg(par + 11); a8 = __ldg(par + 12); }
+    if (have && g.rec) { ra = __ldg(par); a2 = __ldg(par + 10); a4 = __ldg(par + 11); a8 = __ldg(par + 12); }
 
     double acc[YJ][4];
 #pragma unroll
@@ -462,7 +463,7 @@ __global__ void __launch_bounds__(160, 3) ysweep_rec_kernel(const __grid_constan
         const int s = it % NS;
         mbar_wait(&sm.full[s], (it / NS) & 1);
         if (c >= my_cs && c < my_ce) {
-            const int kind = chunk_kind(c, g.w0, Nn, nrows);
+            const int kind = chunk_kind(g.rec, c, g.w0, Nn, nrows);
             if (kind == 1) {
                 // ---- low bulk: G <- a^8 G + sum_r a^(7-r) x_r ----
 #pragma unroll
@@ -521,7 +522,7 @@ __global__ void __launch_bounds__(160, 3) ysweep_rec_kernel(const __grid_constan
     if (!have) return;
 
     // out_t = dense_t + gl_t G + gh_t K; then r_zs interior (df.cpp:377): extended column x -> logical column x + yshift
-    const double* gc = P.ygc + (size_t)g.gc_off * 16;
+    const double* gc = P.ygc + (size_t)(g.rec ? g.gc_off : 0) * 16;      // (mixed groups: G = K = 0, the factors do not matter)
     const int xa0 = t.col0 + 2 * lane;
     const bool vec_ok = ((F.zoff + F.yshift) & 1) == 0;
 #pragma unroll
