@@ -573,3 +573,20 @@ def test_N3_device_scatter_to_cfd_ghost_cells(dfb, W):
     with pytest.raises(dfb.DfbError):
         df.scatter_to_cells(99, pi, gi, d_u)
     df.close()
+
+
+def test_soak_tuned_against_simple_kernels_over_many_steps(dfb, W):
+    """120 back-to-back steps in generate mode (look-ahead noise on the side stream, programmatic launches, work queues, u->v
+    completion stamps all in play) of the tuned kernels against the one-thread-per-cell kernels on the same noise stream: a race
+    anywhere in the tuned path would show up as a divergence (tools/soak.py runs the same at 1024x2048 for 400 steps)."""
+    plane = W.plane_profile(160, 1300, 64, 64)
+    a = dfb.DIGITAL_FILTER(dfb.DFConfig.from_plane(plane, seed=99), fetch=False)
+    b = dfb.DIGITAL_FILTER(dfb.DFConfig.from_plane(plane, seed=99, kernel_variant=1), fetch=False)
+    assert a.tuned and not b.tuned
+    for s in range(120):
+        a.filter(1e-7); b.filter(1e-7)
+        if s % 40 == 39:
+            for w in (dfb.U_FLUC, dfb.V_FLUC, dfb.W_FLUC, dfb.T_FLUC, dfb.RHO_FLUC):
+                ok, r = normwise_close(a.get(w), b.get(w), TOL)
+                assert ok, (s, w, r)
+    a.close(); b.close()
