@@ -204,17 +204,20 @@ def test_G2_generate_mode_equals_oracle_on_the_same_stream(dfb, O, W):
 # ---------------------------------------------------------------------------------------------
 # slabs, state, properties at full size
 # ---------------------------------------------------------------------------------------------
-def test_slabs_reproduce_the_whole_plane_bitwise(dfb, W):
+@pytest.mark.parametrize("ymode", [None, "1"], ids=["y-default", "y-recursive"])
+def test_slabs_reproduce_the_whole_plane_bitwise(dfb, W, monkeypatch, ymode):
     """Slabs whose first column is a multiple of 16 plane columns (what parallel.slab_bounds produces) reproduce the whole plane
     bit for bit, ragged widths included; a slab cut anywhere else takes the direct-form z-sweep and agrees to the G2 tolerance."""
-    plane = W.plane_profile(64, 700, 16, 24)
+    if ymode is not None:
+        monkeypatch.setenv("DFB_Y_MODE", ymode)          # the recursive y kernel must be slab-invariant too (per-column arithmetic)
+    plane = W.plane_profile(64, 700, 16, 24) if ymode is None else W.plane_profile(96, 700, 48, 24)
     whole = dfb.DIGITAL_FILTER(dfb.DFConfig.from_plane(plane, seed=3))
     whole.filter(2e-7); whole.filter(2e-7)
     fields = lambda d: (d.u.fluc, d.v.fluc, d.w.fluc, d.T_fluc, d.rho_fluc)
     for k0, k1 in [(0, 160), (160, 176), (176, 400), (400, 700), (0, 700)]:
         part = dfb.DIGITAL_FILTER(dfb.DFConfig.from_plane(plane, seed=3, k_begin=k0, k_end=k1))
         part.filter(2e-7); part.filter(2e-7)
-        assert (part.Ny, part.Nz) == (64, k1 - k0)
+        assert (part.Ny, part.Nz) == (plane["Ny"], k1 - k0)
         for a, b in zip(fields(part), fields(whole)):
             assert np.array_equal(a, b[:, k0:k1]), (k0, k1)
         part.close()
