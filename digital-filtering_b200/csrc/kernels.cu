@@ -1109,6 +1109,17 @@ int noise_threads() { return NOISE_THREADS * NOISE_PAIRS; }
 int ysweep_rc() { return Y_RC; }
 
 cudaError_t ysweep_prepare() {
+    // One shared-memory carve-out for every kernel of the step: an SM only changes its L1 / shared split when it is idle, so a
+    // noise CTA running with the default split beside the sweeps could leave an SM unable to take its third y-sweep CTA (observed
+    // as a process-wide bimodal y-sweep time on small planes: 26 or 43 us on the reference default plane).
+    {
+        cudaError_t e0 = cudaFuncSetAttribute(noise_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e0 != cudaSuccess) return e0;
+        e0 = cudaFuncSetAttribute(stats_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e0 != cudaSuccess) return e0;
+        e0 = cudaFuncSetAttribute(scatter_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e0 != cudaSuccess) return e0;
+    }
     cudaError_t e = cudaFuncSetAttribute(ysweep_tma_kernel<Y_RC, Y_NS, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(YSmem<Y_RC, Y_NS, 128>));
     if (e != cudaSuccess) return e;
