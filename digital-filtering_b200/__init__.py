@@ -76,6 +76,8 @@ def lib():
         L.dfb_filter.argtypes = [C.c_void_p, C.c_double]
         L.dfb_scatter_to_cells.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
         L.dfb_filter_to_host.argtypes = [C.c_void_p, C.c_double] + [C.c_void_p] * 5
+        L.dfb_filter_to_host_begin.argtypes = [C.c_void_p, C.c_double] + [C.c_void_p] * 5
+        L.dfb_filter_to_host_end.argtypes = [C.c_void_p]
         L.dfb_filter_batch.argtypes = [C.c_void_p, C.c_int, c_dp, C.c_void_p]
         L.dfb_get_field.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.dfb_device_ptr.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]

@@ -57,6 +57,10 @@ struct dfb_filter_s {
     bool injected[3] = {false, false, false};
     cudaStream_t stream = nullptr;    // main stream (high priority): sweeps + epilogue
     cudaStream_t side = nullptr;      // low-priority stream: next step's noise, generated while this step filters
+    cudaStream_t copy = nullptr;      // dfb_filter_to_host_begin/end: device-to-host copies of step t under the compute of step t+1
+    double* stage[2] = {nullptr, nullptr};                 // staged copies of the five output fields
+    cudaEvent_t ev_staged[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+    long long pipe_begun = 0, pipe_ended = 0;
     std::vector<void*> allocs;
     // Two noise buffer sets (r_ys, r_zs): step s uses set s&1, so noise(s+1) can be written while
     // y(s)/z(s) still read set s&1.  D[b] differs from D[1-b] only in the r_ys / r_zs pointers.
@@ -111,6 +115,8 @@ struct dfb_filter_s {
         for (void* p : allocs) cudaFree(p);
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         for (int b = 0; b < 2; ++b) { if (ev_noise[b]) cudaEventDestroy(ev_noise[b]); if (ev_free[b]) cudaEventDestroy(ev_free[b]); }
+        for (int q = 0; q < 2; ++q) { if (ev_staged[q]) cudaEventDestroy(ev_staged[q]); if (ev_copied[q]) cudaEventDestroy(ev_copied[q]); }
+        if (copy) cudaStreamDestroy(copy);
         if (side) cudaStreamDestroy(side);
         if (stream) cudaStreamDestroy(stream);
     }
@@ -842,6 +848,46 @@ int dfb_filter_to_host(dfb_handle h, double dt, double* u, double* v, double* w,
         for (int i = 0; i < 5; ++i)
             if (dst[i]) CUDA_TRY(cudaMemcpyAsync(dst[i], field_ptr(*h, i), bytes, cudaMemcpyDeviceToHost, h->stream));
         CUDA_TRY(cudaStreamSynchronize(h->stream));
+    });
+}
+
+int dfb_filter_to_host_begin(dfb_handle h, double dt, double* u, double* v, double* w, double* T, double* rho) {
+    if (!h) return fail(DFB_ERR_ARG, "handle is NULL");
+    return guarded([&] {
+        if (h->pipe_begun - h->pipe_ended >= 2) throw Error{DFB_ERR_STATE, "two dfb_filter_to_host_begin calls are already outstanding: call dfb_filter_to_host_end first"};
+        CUDA_TRY(cudaSetDevice(h->device));
+        const size_t n = (size_t)h->D[0].Ny * h->D[0].W, bytes = n * sizeof(double);
+        const int p = (int)(h->pipe_begun & 1);
+        if (!h->copy) {
+            CUDA_TRY(cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking));
+            for (int q = 0; q < 2; ++q) {
+                h->stage[q] = h->dalloc<double>(5 * n, false);
+                CUDA_TRY(cudaEventCreateWithFlags(&h->ev_staged[q], cudaEventDisableTiming));
+                CUDA_TRY(cudaEventCreateWithFlags(&h->ev_copied[q], cudaEventDisableTiming));
+            }
+        }
+        run_step(*h, dt, false);
+        // stage the five fields (device to device, on the compute stream: the next step may then overwrite them), then copy the
+        // staged set to the caller's arrays on the copy stream while the next step computes
+        CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_copied[p], 0));          // the copy that last read this staging set (a no-op before its first use)
+        double* dst[5] = {u, v, w, T, rho};
+        for (int i = 0; i < 5; ++i)
+            if (dst[i]) CUDA_TRY(cudaMemcpyAsync(h->stage[p] + (size_t)i * n, field_ptr(*h, i), bytes, cudaMemcpyDeviceToDevice, h->stream));
+        CUDA_TRY(cudaEventRecord(h->ev_staged[p], h->stream));
+        CUDA_TRY(cudaStreamWaitEvent(h->copy, h->ev_staged[p], 0));
+        for (int i = 0; i < 5; ++i)
+            if (dst[i]) CUDA_TRY(cudaMemcpyAsync(dst[i], h->stage[p] + (size_t)i * n, bytes, cudaMemcpyDeviceToHost, h->copy));
+        CUDA_TRY(cudaEventRecord(h->ev_copied[p], h->copy));
+        h->pipe_begun += 1;
+    });
+}
+
+int dfb_filter_to_host_end(dfb_handle h) {
+    if (!h) return fail(DFB_ERR_ARG, "handle is NULL");
+    return guarded([&] {
+        if (h->pipe_ended >= h->pipe_begun) throw Error{DFB_ERR_STATE, "no dfb_filter_to_host_begin is outstanding"};
+        CUDA_TRY(cudaEventSynchronize(h->ev_copied[(int)(h->pipe_ended & 1)]));
+        h->pipe_ended += 1;
     });
 }
 

@@ -118,6 +118,11 @@ int dfb_first_step(dfb_handle h);
 /* filter(dt) + copy the five outputs into caller (host) arrays of Ny*Nz doubles; any pointer may be
  * NULL.  This is the call the C++ / Fortran facades make every step (u.fluc ... live on the host). */
 int dfb_filter_to_host(dfb_handle h, double dt, double* u, double* v, double* w, double* T, double* rho);
+/* The same, pipelined: _begin enqueues the step and the copies and returns; _end blocks until the arrays of the OLDEST outstanding
+ * _begin are filled.  At most two _begin may be outstanding, so a caller with two sets of (pinned) arrays overlaps the copy of step t
+ * (84 MB at 1024x2048: 1.5 ms of PCIe) with the compute of step t+1:  begin(A); loop { begin(B); end(); use A; swap(A, B); } */
+int dfb_filter_to_host_begin(dfb_handle h, double dt, double* u, double* v, double* w, double* T, double* rho);
+int dfb_filter_to_host_end(dfb_handle h);
 /* nsteps consecutive steps; out (optional, host) receives [nsteps][5][Ny*Nz] with D2H copies
  * overlapped with the following steps. */
 int dfb_filter_batch(dfb_handle h, int nsteps, const double* dt, double* out);

@@ -593,3 +593,30 @@ def test_soak_tuned_against_simple_kernels_over_many_steps(dfb, W):
                 ok, r = normwise_close(a.get(w), b.get(w), TOL)
                 assert ok, (s, w, r)
     a.close(); b.close()
+
+
+def test_pipelined_filter_to_host_delivers_every_step(dfb, W):
+    """dfb_filter_to_host_begin/_end (copy of step t under the compute of step t+1, two sets of host arrays) against the
+    synchronous dfb_filter_to_host on a twin handle: same five fields for every step; a third outstanding begin is refused."""
+    import ctypes as C
+    plane = W.plane_profile(48, 200, 12, 10)
+    a = dfb.DIGITAL_FILTER(dfb.DFConfig.from_plane(plane, seed=41), fetch=False)
+    b = dfb.DIGITAL_FILTER(dfb.DFConfig.from_plane(plane, seed=41), fetch=False)
+    L = dfb.lib()
+    n = 48 * 200
+    sets = [[np.zeros(n) for _ in range(5)] for _ in range(2)]
+    ref = [np.zeros(n) for _ in range(5)]
+    ptrs = lambda arrs: [x.ctypes.data_as(C.c_void_p) for x in arrs]
+    dts = [1e-7, 2e-7, 3e-7, 1e-7, 2e-7]
+    dfb._check(L.dfb_filter_to_host_begin(a._h, dts[0], *ptrs(sets[0])))
+    for i in range(1, len(dts) + 1):
+        if i < len(dts):
+            dfb._check(L.dfb_filter_to_host_begin(a._h, dts[i], *ptrs(sets[i & 1])))
+        if i == 1:
+            assert L.dfb_filter_to_host_begin(a._h, 1e-7, *ptrs(sets[0])) != 0          # two are outstanding
+        dfb._check(L.dfb_filter_to_host_end(a._h))                                       # step i-1 has arrived
+        dfb._check(L.dfb_filter_to_host(b._h, dts[i - 1], *ptrs(ref)))
+        for x, y in zip(sets[(i - 1) & 1], ref):
+            assert np.array_equal(x, y), i
+    assert L.dfb_filter_to_host_end(a._h) != 0                                           # nothing outstanding
+    a.close(); b.close()
