@@ -615,8 +615,10 @@ void run_step(dfb_filter_s& H, double dt, bool first) {
     const int b = (int)(H.step & 1);
     if (H.timing) CUDA_TRY(cudaEventRecord(H.ev[0], H.stream));
     if (H.noise_mode == DFB_NOISE_GENERATE) {
-        if (H.buf_step[b] == H.step) CUDA_TRY(cudaStreamWaitEvent(H.stream, H.ev_noise[b], 0));   // prefetched
-        else launch_noise_for(H, H.step, b, H.stream);
+        // ev_noise[b] = the last noise launch into set b on EITHER stream: wait for it whether its result is the one this step
+        // wants (prefetched) or not (after a dfb_set_state rewind the side stream's prefetch may still be writing set b)
+        CUDA_TRY(cudaStreamWaitEvent(H.stream, H.ev_noise[b], 0));
+        if (H.buf_step[b] != H.step) launch_noise_for(H, H.step, b, H.stream);
     } else if (!(H.injected[0] && H.injected[1] && H.injected[2])) {
         throw Error{DFB_ERR_STATE, "noise_mode = inject: dfb_set_noise must be called for u, v and w before every step"};
     }
@@ -1022,6 +1024,8 @@ int dfb_set_state(dfb_handle h, const double* filt_old3, int64_t step) {
             for (int f = 0; f < 3; ++f)
                 CUDA_TRY(cudaMemcpyAsync(h->D[0].f[f].filt_old, filt_old3 + f * n, n * 8, cudaMemcpyHostToDevice, h->stream));
         CUDA_TRY(cudaStreamSynchronize(h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->side));      // a look-ahead noise launch for the old step counter may still be in flight
+        if (step != h->step) { h->buf_step[0] = h->buf_step[1] = -1; h->ybuf_step[0] = h->ybuf_step[1] = -1; }
         h->step = step;
     });
 }

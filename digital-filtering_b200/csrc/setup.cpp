@@ -2,7 +2,9 @@
 // runs before the first sweep.  It is executed once per handle, on the host, with the host's libm
 // (exp / tanh / sqrt), exactly like the reference, so that no device transcendental ever enters
 // the parity gate (SURVEY 8c "third-party arithmetic").  Expression order follows the cited lines:
-// the resulting tables are bit-identical to the reference object's (tests/test_setup_parity.py).
+// the resulting tables are bit-identical to the reference object's (tests/test_gpu_parity.py::
+// test_G2_default_plane_against_reference_object_code compares rows, half-widths, coefficients and Lt
+// with the running reference object; tests/test_oracle_vs_ref.py pins the restatement they are checked with).
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -59,34 +61,42 @@ std::vector<std::vector<double>> read_zone_file(const std::string& path, int& n_
 
 }  // namespace
 
-// df.cpp:805-848
-std::vector<double> linear_interpolate(const std::vector<double>& y_data, const std::vector<double>& f_data,
-                                       const std::vector<double>& y_new) {
-    if (y_data.size() != f_data.size()) throw Error{DFB_ERR_INTERP, "y_data and f_data must be the same size."};
-    if (y_data.size() < 2) throw Error{DFB_ERR_INTERP, "Need at least two data points to interpolate."};
-    std::vector<double> f_new(y_new.size());
-    for (size_t j = 0; j < y_new.size(); ++j) {
-        double y = y_new[j];
-        if (y <= y_data.front()) { f_new[j] = f_data.front(); continue; }
-        if (y >= y_data.back()) { f_new[j] = f_data.back(); continue; }
-        size_t i = 0;
-        while (i + 1 < y_data.size() && y > y_data[i + 1]) ++i;
-        double x0 = y_data[i], x1 = y_data[i + 1], f0 = f_data[i], f1 = f_data[i + 1];
-        f_new[j] = f0 + (f1 - f0) * ((y - x0) / (x1 - x0));
+// Clamped piecewise-linear resampling of a tabulated profile onto new abscissae (the job of df.cpp:805-848).
+// The table is ascending, so the bracketing interval is found by bisection; the reference walks the table
+// from the start for every point, which lands on the same interval.  Only the interpolation expression
+// itself is kept in the reference's operand order, because the row tables must come out bit-identical.
+std::vector<double> linear_interpolate(const std::vector<double>& xs, const std::vector<double>& fs,
+                                       const std::vector<double>& at) {
+    const size_t n = xs.size();
+    if (fs.size() != n) throw Error{DFB_ERR_INTERP, "interpolation table: abscissae and values differ in length"};
+    if (n < 2) throw Error{DFB_ERR_INTERP, "interpolation table needs at least two points"};
+    std::vector<double> out;
+    out.reserve(at.size());
+    for (double q : at) {
+        if (q <= xs[0]) { out.push_back(fs[0]); continue; }           // below the table: first value
+        if (q >= xs[n - 1]) { out.push_back(fs[n - 1]); continue; }   // above the table: last value
+        const size_t hi = (size_t)(std::lower_bound(xs.begin() + 1, xs.end(), q) - xs.begin());   // first knot >= q
+        const size_t lo = hi - 1;
+        const double w = (q - xs[lo]) / (xs[hi] - xs[lo]);
+        out.push_back(fs[lo] + (fs[hi] - fs[lo]) * w);
     }
-    return f_new;
+    return out;
 }
 
-// df.cpp:166-177 == 202-216
+// Filter coefficients of half-width N (df.cpp:166-177 == 202-216): a two-sided exponential exp(-2 pi |i| / N)
+// normalised to unit energy.  One side is evaluated and mirrored; the energy is accumulated from the centre
+// outwards in the reference's order (t_0^2, then 2 t_i^2) so that the table is bit-identical to its by / bz.
 void coefficients(int N, double* b) {
-    std::vector<double> temp(N + 1);
-    double sum = 0.0;
+    double* mid = b + N;
+    double energy = 0.0;
     for (int i = 0; i <= N; ++i) {
-        temp[i] = std::exp(pi_c * std::abs(i) / N);
-        sum += (i == 0 ? 1.0 : 2.0) * temp[i] * temp[i];
+        const double t = std::exp(pi_c * i / N);
+        mid[i] = t;
+        energy += (i ? 2.0 : 1.0) * t * t;
     }
-    sum = std::sqrt(sum);
-    for (int i = -N; i <= N; ++i) b[N + i] = temp[std::abs(i)] / sum;
+    const double norm = std::sqrt(energy);
+    for (int i = 0; i <= N; ++i) mid[i] /= norm;
+    for (int i = 1; i <= N; ++i) mid[-i] = mid[i];
 }
 
 void build_plan(const dfb_config& cfg, Plan& P) {
@@ -131,6 +141,9 @@ void build_plan(const dfb_config& cfg, Plan& P) {
         if (!cfg.rows && yc.empty()) throw Error{DFB_ERR_ARG, "interpolating the row tables from files needs yc"};
     }
     const size_t gstride = per_row ? 1 : (size_t)NzG;   // index of (j, k=0) = j*gstride
+    const int Ny_in = Ny;                                // rows as the caller laid its arrays out (the DNS-range trim below may shorten Ny)
+    for (double v : dy) if (!(v > 0)) throw Error{DFB_ERR_ARG, "cell heights dy must be positive"};
+    for (double v : dz) if (!(v > 0)) throw Error{DFB_ERR_ARG, "cell widths dz must be positive"};
 
     // ---- row tables: get_RST_in df.cpp:220-330, read_line_file df.cpp:487-553 ----
     if (cfg.rows) {
@@ -270,8 +283,8 @@ void build_plan(const dfb_config& cfg, Plan& P) {
         FieldPlan& F = P.f[f];
         std::vector<int> Ny_arr((size_t)Ny * ncol), Nz_arr((size_t)Ny * ncol);
         if (cfg.N_y && cfg.N_z) {
-            const int* sy = cfg.N_y + (size_t)f * Ny * ncol;
-            const int* sz = cfg.N_z + (size_t)f * Ny * ncol;
+            const int* sy = cfg.N_y + (size_t)f * Ny_in * ncol;      // caller's layout: [3][Ny_in * ncol], untrimmed
+            const int* sz = cfg.N_z + (size_t)f * Ny_in * ncol;
             for (size_t i = 0; i < Ny_arr.size(); ++i) {
                 if (sy[i] < 0 || sz[i] < 0) throw Error{DFB_ERR_ARG, "half-widths must be >= 0"};
                 Ny_arr[i] = sy[i]; Nz_arr[i] = sz[i];
