@@ -67,6 +67,15 @@ def lib():
         L.dfb_last_error.restype = C.c_char_p
         L.dfb_version.restype = C.c_char_p
         L.dfb_create.argtypes = [C.POINTER(dfb_config), C.POINTER(C.c_void_p)]
+        L.dfb_create_batch.argtypes = [C.POINTER(dfb_config), C.c_int, C.POINTER(C.c_void_p)]
+        L.dfb_num_planes.argtypes = [C.c_void_p, c_ip]
+        L.dfb_get_field_plane.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.dfb_device_ptr_plane.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.dfb_stats_get_plane.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, c_dp, C.POINTER(C.c_int64)]
+        L.dfb_get_rms.argtypes = [C.c_void_p, C.c_int, C.c_double]
+        L.dfb_write_rms_csv.argtypes = [C.c_void_p, C.c_char_p]
+        L.dfb_write_tecplot.argtypes = [C.c_void_p, C.c_char_p]
+        L.dfb_face_map.argtypes = [C.c_void_p, C.c_int, c_dp, c_dp, c_ip]
         for name in ("dfb_destroy", "dfb_sync", "dfb_first_step"):
             getattr(L, name).argtypes = [C.c_void_p]
         L.dfb_dims.argtypes = [C.c_void_p, c_ip, c_ip]
@@ -187,7 +196,10 @@ class DIGITAL_FILTER:
     """DIGITAL_FILTER (df.hpp:52-125) on one B200.  Construction = df.cpp:4-66 (setup + first step);
     filter(dt) = df.cpp:449-468 without the print and the CSV."""
 
-    def __init__(self, config=None, fetch=True):
+    def __init__(self, config=None, fetch=True, nplanes=1):
+        """nplanes > 1: a batch of independent planes of this geometry advanced by one launch set per step (dfb_create_batch,
+        BASELINE config 5); plane p draws from stream group config.plane_id + p.  The host members then describe plane 0;
+        get(which, plane=p) / device_ptr(which, plane=p) reach the others."""
         config = config or DFConfig()
         L = lib()
         c = dfb_config()
@@ -218,7 +230,12 @@ class DIGITAL_FILTER:
         c.k_begin, c.k_end = config.k_begin, config.k_end
         c.skip_first_step, c.kernel_variant = config.skip_first_step, config.kernel_variant
         self._h = C.c_void_p()
-        _check(L.dfb_create(C.byref(c), C.byref(self._h)))
+        self.nplanes = int(nplanes)
+        if self.nplanes == 1:
+            _check(L.dfb_create(C.byref(c), C.byref(self._h)))
+        else:
+            _check(L.dfb_create_batch(C.byref(c), self.nplanes, C.byref(self._h)))
+            fetch = False
         ny, nz = C.c_int(), C.c_int()
         _check(L.dfb_dims(self._h, C.byref(ny), C.byref(nz)))
         self.Ny, self.Nz, self.n_cells = ny.value, nz.value, ny.value * nz.value
@@ -263,17 +280,17 @@ class DIGITAL_FILTER:
         _check(lib().dfb_filter_batch(self._h, len(dts), _dptr(dts), out.ctypes.data if out is not None else None))
 
     # ---- data access ----
-    def get(self, which, out=None):
+    def get(self, which, out=None, plane=0):
         out = np.zeros((self.Ny, self.Nz)) if out is None else out
-        _check(lib().dfb_get_field(self._h, which, out.ctypes.data, 0))
+        _check(lib().dfb_get_field_plane(self._h, plane, which, out.ctypes.data, 0))
         return out
 
     def get_to_device(self, which, device_ptr):
         _check(lib().dfb_get_field(self._h, which, C.c_void_p(device_ptr), 1))
 
-    def device_ptr(self, which):
+    def device_ptr(self, which, plane=0):
         p = C.c_void_p()
-        _check(lib().dfb_device_ptr(self._h, which, C.byref(p)))
+        _check(lib().dfb_device_ptr_plane(self._h, plane, which, C.byref(p)))
         return p.value
 
     def device_tensor(self, which):
@@ -366,7 +383,7 @@ class DIGITAL_FILTER:
 
     # ---- checkpoint ----
     def get_state(self):
-        fo = np.zeros((3, self.Ny, self.Nz))
+        fo = np.zeros((3, self.Ny, self.Nz)) if self.nplanes == 1 else np.zeros((3, self.nplanes, self.Ny, self.Nz))
         s = C.c_int64()
         _check(lib().dfb_get_state(self._h, _dptr(fo), C.byref(s)))
         return fo, s.value
@@ -379,16 +396,33 @@ class DIGITAL_FILTER:
     def stats_enable(self, on=True):
         _check(lib().dfb_stats_enable(self._h, int(on)))
 
-    def stats(self, which, rms=False):
+    def stats(self, which, rms=False, plane=0):
         """which: 0 u'^2, 1 v'^2, 2 w'^2, 3 T'^2, 4 rho'^2, 5 u'v' (per-cell sums, or sqrt(sum/count) with rms=True).
         Returns (array, accumulated steps)."""
         out = np.zeros((self.Ny, self.Nz))
         cnt = C.c_int64()
-        _check(lib().dfb_stats_get(self._h, which, int(rms), _dptr(out), C.byref(cnt)))
+        _check(lib().dfb_stats_get_plane(self._h, plane, which, int(rms), _dptr(out), C.byref(cnt)))
         return out, cnt.value
+
+    def get_rms(self, nsteps=500, dt=1e-5, path=None):
+        """get_rms (df.cpp:584-611): 500 steps of dt = 1e-5 with on-device accumulation; plot_rms's file when `path` is given."""
+        _check(lib().dfb_get_rms(self._h, int(nsteps), float(dt)))
+        if path is not None:
+            _check(lib().dfb_write_rms_csv(self._h, str(path).encode()))
 
     def write_csv(self, path):
         _check(lib().dfb_write_csv(self._h, str(path).encode()))
+
+    def write_tecplot(self, path):
+        _check(lib().dfb_write_tecplot(self._h, str(path).encode()))
+
+    def face_map(self, yf, zf):
+        """plane_index (j*Nz + k within this handle's slab, -1 outside it) of the cells containing the face centres (yf, zf)"""
+        yf = np.ascontiguousarray(yf, dtype=np.float64)
+        zf = np.ascontiguousarray(zf, dtype=np.float64)
+        out = np.zeros(len(yf), dtype=np.int32)
+        _check(lib().dfb_face_map(self._h, len(yf), _dptr(yf), _dptr(zf), out.ctypes.data_as(c_ip)))
+        return out
 
     # ---- timing ----
     def set_timing(self, on=True):

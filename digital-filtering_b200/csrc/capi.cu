@@ -52,8 +52,8 @@ struct dfb_filter_s {
     bool tuned = false;
     uint64_t seed = 0;
     int plane_id = 0;
+    int nplanes = 1;                  // planes advanced together by this handle (dfb_create_batch): plane p draws from stream group plane_id + p
     int64_t step = 0;                 // steps completed (the constructor's first step counts as one)
-    int z_launches = 0;               // stamp of the z-sweep's u->v completion flags: never rewinds (dfb_set_state may rewind `step`)
     bool injected[3] = {false, false, false};
     cudaStream_t stream = nullptr;    // main stream (high priority): sweeps + epilogue
     cudaStream_t side = nullptr;      // low-priority stream: next step's noise, generated while this step filters
@@ -86,7 +86,7 @@ struct dfb_filter_s {
     NoiseParams np{};
     unsigned long long* tl = nullptr; // development aid (DFB_TIMELINE): 64 steps x {noise, y, z} x {start, end}
     // N2: running statistics (opt-in)
-    double* stats = nullptr;          // [6][Ny*W]: sum u'^2, v'^2, w'^2, T'^2, rho'^2, u'v'
+    double* stats = nullptr;          // [P][6][Ny*W]: sum u'^2, v'^2, w'^2, T'^2, rho'^2, u'v'
     int64_t stats_count = 0;
     bool stats_on = false;
     // timing
@@ -147,6 +147,8 @@ void build_device(dfb_filter_s& H) {
     PlaneDev& D = H.D[0];
     const int Ny = P.Ny, W = P.Nz(), NzG = P.NzG;
     D.Ny = Ny; D.W = W; D.NzG = NzG; D.k0 = P.k0;
+    const int NP = H.nplanes;
+    D.P = NP; D.ps_cells = (size_t)Ny * W;
     H.tuned = (H.kernel_variant == 0) && P.f[0].row_uniform && P.f[1].row_uniform && P.f[2].row_uniform;
 
     // ---- per-row epilogue constants, reference expressions (df.cpp:425-438, 474) ----
@@ -167,8 +169,8 @@ void build_device(dfb_filter_s& H) {
     D.rowc = H.upload(rowc);
     D.coef_ptr = H.upload(P.coef.ptr);
     D.coef_vals = H.upload(P.coef.vals);
-    D.T_fluc = H.dalloc<double>((size_t)Ny * W);
-    D.rho_fluc = H.dalloc<double>((size_t)Ny * W);
+    D.T_fluc = H.dalloc<double>((size_t)NP * Ny * W);
+    D.rho_fluc = H.dalloc<double>((size_t)NP * Ny * W);
 
     int maxNz = 0;
     for (int f = 0; f < 3; ++f) {
@@ -184,10 +186,12 @@ void build_device(dfb_filter_s& H) {
         F.zoff = (16 - FP.Nz_max % 16) % 16;
         F.pitch_z = round_up(F.zoff + W + 2 * FP.Nz_max, 16) + 16;
         F.yshift = F.xk0 - P.k0 + FP.Nz_max;
-        F.r_ys = H.dalloc<double>((size_t)F.rows_y * F.pitch_y);
-        F.r_zs = H.dalloc<double>((size_t)Ny * F.pitch_z);
-        F.filt_old = H.dalloc<double>((size_t)Ny * W);
-        F.fluc = H.dalloc<double>((size_t)Ny * W);
+        F.ps_ys = (size_t)F.rows_y * F.pitch_y;
+        F.ps_zs = (size_t)Ny * F.pitch_z;
+        F.r_ys = H.dalloc<double>(NP * F.ps_ys);
+        F.r_zs = H.dalloc<double>(NP * F.ps_zs);
+        F.filt_old = H.dalloc<double>((size_t)NP * Ny * W);
+        F.fluc = H.dalloc<double>((size_t)NP * Ny * W);
         F.Ny_row = H.upload(FP.N_y_row);
         F.Nz_row = H.upload(FP.N_z_row);
         F.Ny_cell = FP.row_uniform ? nullptr : H.upload(FP.N_y);
@@ -195,8 +199,8 @@ void build_device(dfb_filter_s& H) {
     }
     H.D[1] = H.D[0];
     for (int f = 0; f < 3; ++f) {
-        H.D[1].f[f].r_ys = H.dalloc<double>((size_t)D.f[f].rows_y * D.f[f].pitch_y);
-        H.D[1].f[f].r_zs = H.dalloc<double>((size_t)Ny * D.f[f].pitch_z);
+        H.D[1].f[f].r_ys = H.dalloc<double>(NP * D.f[f].ps_ys);
+        H.D[1].f[f].r_zs = H.dalloc<double>(NP * D.f[f].ps_zs);
     }
 
     // ---- tuned y-sweep: row groups, dense band matrices, work items, TMA maps ----
@@ -396,7 +400,7 @@ void build_device(dfb_filter_s& H) {
         for (int b = 0; b < 2; ++b)
         for (int f = 0; f < 3; ++f) {
             const FieldDev& F = H.D[b].f[f];
-            cuuint64_t dims[2] = {(cuuint64_t)F.We, (cuuint64_t)F.rows_y};
+            cuuint64_t dims[2] = {(cuuint64_t)F.We, (cuuint64_t)F.rows_y * (cuuint64_t)NP};      // planes of a batch stacked along the rows
             cuuint64_t strides[1] = {(cuuint64_t)F.pitch_y * sizeof(double)};
             cuuint32_t box[2] = {(cuuint32_t)ytk, (cuuint32_t)RC};
             cuuint32_t estr[2] = {1u, 1u};
@@ -455,50 +459,60 @@ void build_device(dfb_filter_s& H) {
             Z.coef_pad_ptr = H.upload(pptr);
             Z.box_lines = maxlines;
             Z.box_bytes = maxlines * ZKc * 8;
-            Z.unit_bytes = round_up(Z.box_bytes + maxcoef * 8, ZKc == 16 ? 1024 : 512);   // the swizzle pattern repeats every 1024 (512) bytes
-            Z.smem_bytes = 4 * 2 * Z.unit_bytes + 4 * 2 * 8 + 4 * 2 * 64 + 1024;   // buffers, mbarriers, item descriptors, alignment slack
-            if (maxlines > 256) throw Error{DFB_ERR_ARG, "z half-width too large for the staged window"};
-            // Units (row, strip, field) pulled from a counter by the persistent warps.  v' needs u's blended field
-            // (df.cpp:437): every u unit comes first (most expensive first), then w, then v; a v unit checks the
-            // completion flag of its u unit (set long before in practice; u units never wait, so no deadlock).
-            std::vector<ZUnit> units;
-            const int nstrips = (W + strip - 1) / strip;
-            const int forder[3] = {0, 2, 1};
-            for (int fi = 0; fi < 3; ++fi) {
-                const int f = forder[fi];
-                std::vector<ZUnit> group;
-                for (int j = 0; j < Ny; ++j) {
-                    const int N = P.f[f].N_z_row[j];
-                    const int d = ((-N) % ZKc + ZKc) % ZKc;
-                    ZUnit u{};
-                    u.j = j; u.f = f;
-                    u.nchunk = 1 + (2 * N + d + ZKc - 1) / ZKc;
-                    u.cbytes = (round_up((u.nchunk + 1) * ZKc, 16) + 16) * (int)sizeof(double);
-                    u.coff16 = (int)(pptr[N] / 16);
-                    const FieldDev& F = H.D[0].f[f];
-                    for (int si = 0; si < nstrips; ++si) {
-                        u.c0 = si * strip;
-                        u.line0 = (F.zoff + u.c0 + F.Nz_max - N) / ZKc;      // that column is d past a line boundary by construction
-                        u.flag = j * nstrips + si;
-                        group.push_back(u);
-                    }
-                }
-                std::stable_sort(group.begin(), group.end(), [](const ZUnit& a, const ZUnit& b2) { return a.nchunk > b2.nchunk; });
-                units.insert(units.end(), group.begin(), group.end());
-            }
-            Z.units = H.upload(units);
-            Z.n_units = (int)units.size();
+            // Recursive evaluation of the truncated two-sided exponential (see the kernel) unless the slab starts or ends off a
+            // 16-column boundary of the plane (its lane blocks would differ from the whole plane's: results would agree to
+            // ~1e-14 but not bit for bit) or a row has N = 0.  DFB_Z_MODE=0 forces the direct Toeplitz form.
             {
-                // Recursive evaluation of the truncated two-sided exponential (see the kernel) unless the slab starts or ends off a
-                // 16-column boundary of the plane (its lane blocks would differ from the whole plane's: results would agree to
-                // ~1e-14 but not bit for bit) or a row has N = 0.  DFB_Z_MODE=0 forces the direct Toeplitz form.
                 bool rec = (P.k0 % 16) == 0 && (P.k1 % 16 == 0 || P.k1 == P.NzG);
                 for (int f = 0; f < 3; ++f) for (int v : P.f[f].N_z_row) rec = rec && v >= 1;
                 const char* zm = std::getenv("DFB_Z_MODE");
                 Z.zmode = zm ? std::atoi(zm) : (rec ? 1 : 0);
                 if (Z.zmode == 1 && !rec) throw Error{DFB_ERR_ARG, "DFB_Z_MODE=1 needs slab boundaries on multiples of 16 columns and N_z >= 1"};
             }
-            Z.flags = H.dalloc<int>((size_t)Ny * nstrips);
+            // what is staged after the window: the whole padded coefficient vector (direct form) or only its 128-byte header line
+            const int tailcoef = Z.zmode == 1 ? 16 : maxcoef;
+            Z.rc_off = Z.box_bytes + tailcoef * 8;                        // row constants: 64 bytes
+            Z.fo_off = round_up(Z.rc_off + ROWC * 8, 128);                // staged strip of filt_old: 32 lines
+            Z.unit_bytes = round_up(Z.fo_off + 32 * ZKc * 8, ZKc == 16 ? 1024 : 512);   // the swizzle pattern repeats every 1024 (512) bytes
+            // per warp: two staging buffers + the u line buffer (32 lines); then mbarriers, item descriptors (2 x 2 x 8 ints per warp), alignment slack
+            Z.smem_bytes = 4 * (2 * Z.unit_bytes + 32 * ZKc * 8) + 64 + 4 * 32 * 4 + 1024;
+            if (maxlines > 256) throw Error{DFB_ERR_ARG, "z half-width too large for the staged window"};
+            // Work items pulled from a counter by the persistent warps: per (row, strip) the pair of units (u, v) -- v' needs u's
+            // blended field (df.cpp:437), which the u unit leaves in the warp's shared-memory line buffer for the v unit that
+            // follows it -- and the unit w as an item of its own.
+            std::vector<ZUnit> units;
+            const int nstrips = (W + strip - 1) / strip;
+            struct Item { int j, si, cost; };
+            std::vector<Item> items;
+            for (int j = 0; j < Ny; ++j)
+                for (int si = 0; si < nstrips; ++si) items.push_back(Item{j, si, 0});
+            auto make_unit = [&](const Item& it, int f) {
+                const int N = P.f[f].N_z_row[it.j];
+                const int d = ((-N) % ZKc + ZKc) % ZKc;
+                const int clen = round_up((1 + (2 * N + d + ZKc - 1) / ZKc + 1) * ZKc, 16) + 16;
+                ZUnit u{};
+                u.j = it.j; u.f = f;
+                u.nchunk = 1 + (2 * N + d + ZKc - 1) / ZKc;
+                if (Z.zmode == 1) { u.cbytes = 16 * (int)sizeof(double); u.coff16 = (int)((pptr[N] + clen - 16) / 16); }
+                else { u.cbytes = clen * (int)sizeof(double); u.coff16 = (int)(pptr[N] / 16); }
+                const FieldDev& F = H.D[0].f[f];
+                u.c0 = it.si * strip;
+                u.line0 = (F.zoff + u.c0 + F.Nz_max - N) / ZKc;      // that column is d past a line boundary by construction
+                return u;
+            };
+            // pairs (u, v) first, then the w units on their own: the tail of the queue is one unit long
+            auto by_cost = [&](int fa, int fb) {
+                std::vector<Item> v = items;
+                for (Item& it : v) it.cost = P.f[fa].N_z_row[it.j] + (fb >= 0 ? P.f[fb].N_z_row[it.j] : 0);
+                std::stable_sort(v.begin(), v.end(), [](const Item& a, const Item& b2) { return a.cost > b2.cost; });
+                return v;
+            };
+            for (const Item& it : by_cost(0, 1)) { units.push_back(make_unit(it, 0)); units.push_back(make_unit(it, 1)); }
+            for (const Item& it : by_cost(2, -1)) units.push_back(make_unit(it, 2));
+            units.push_back(ZUnit{});                                // the last single item is fetched as 8 ints: nothing to pad, but keep the array non-empty-safe
+            Z.units = H.upload(units);
+            Z.n_uv = (int)items.size();
+            Z.n_items = 2 * (int)items.size();
             Z.counter = H.dalloc<int>(2);        // one work counter per buffer set: y(s+1) resets its own while z(s) still pulls from the other
             Z.debug = std::getenv("DFB_DEBUG_Z") ? std::atoi(std::getenv("DFB_DEBUG_Z")) : 0;
             Z.prof = H.dalloc<unsigned long long>(4096);
@@ -511,14 +525,14 @@ void build_device(dfb_filter_s& H) {
             // then run beside the sweep instead of after it (measured: 0.168 vs 0.176 ms/step on 1024x2048 profile).
             if (Z.zmode == 1 && Z.zk == 16) zb = std::min(zb, 2);
             if (std::getenv("DFB_Z_BLOCKS_PER_SM")) zb = std::min(std::max(zb, 3), std::atoi(std::getenv("DFB_Z_BLOCKS_PER_SM")));
-            Z.nblocks = std::max(1, std::min(std::max(zb, 1) * prop.multiProcessorCount, (Z.n_units + 3) / 4));
+            Z.nblocks = std::max(1, std::min(std::max(zb, 1) * prop.multiProcessorCount, (Z.n_items * NP + 3) / 4));
             Z.n_sm = prop.multiProcessorCount;
             H.yp[0].zcounter = Z.counter;
             H.yp[1].zcounter = Z.counter + 1;
             for (int b = 0; b < 2; ++b)
                 for (int f = 0; f < 3; ++f) {
                     const FieldDev& F = H.D[b].f[f];
-                    cuuint64_t dims[3] = {(cuuint64_t)Z.zk, (cuuint64_t)(F.pitch_z / Z.zk), (cuuint64_t)Ny};
+                    cuuint64_t dims[3] = {(cuuint64_t)Z.zk, (cuuint64_t)(F.pitch_z / Z.zk), (cuuint64_t)Ny * (cuuint64_t)NP};
                     cuuint64_t strides[2] = {(cuuint64_t)Z.zk * 8, (cuuint64_t)F.pitch_z * sizeof(double)};
                     cuuint32_t box[3] = {(cuuint32_t)Z.zk, (cuuint32_t)Z.box_lines, 1u};
                     cuuint32_t estr[3] = {1u, 1u, 1u};
@@ -585,12 +599,19 @@ void fill_noise_params(dfb_filter_s& H, int64_t step) {
     int n = 0;
     for (const NoiseHost& A : H.noise) {
         if (!A.n_seg) continue;
-        NoiseArray& a = H.np.a[n++];
-        const Jump j = pcg_jump(4u * ((uint64_t)step * A.npairs), A.inc);
-        a.state = j.A * A.state0 + j.C;
-        a.inc = A.inc;
+        NoiseArray& a = H.np.a[n];
         a.seg_jump = A.d_jump; a.seg_q0 = static_cast<const long long*>(A.d_q0); a.seg_np = static_cast<const int*>(A.d_np);
         a.n_seg = A.n_seg; a.kind = A.kind; a.field = A.field;
+        for (int p = 0; p < H.nplanes; ++p) {
+            // stream ((plane*3 + field)*2 + array) of include/dfb_rng_spec.h; plane p of a batch is plane_id + p
+            const uint64_t stream = (uint64_t)((((int64_t)H.plane_id + p) * 3 + A.field) * 2 + A.kind);
+            const uint64_t inc = (stream << 1) | 1u;
+            const uint64_t state0 = pcg_lcg(H.seed + inc, inc);
+            const Jump j = pcg_jump(4u * ((uint64_t)step * A.npairs), inc);
+            H.np.pstate[p][n] = j.A * state0 + j.C;
+            H.np.pinc[p][n] = inc;
+        }
+        ++n;
     }
     H.np.n_arrays = n;
 }
@@ -638,9 +659,16 @@ void run_step(dfb_filter_s& H, double dt, bool first) {
         S.sa[f] = std::sqrt(alpha);                                // df.cpp:415
         S.sb[f] = std::sqrt(1.0 - alpha);
     }
-    if (H.tuned) { H.zp[b].S = S; H.zp[b].stamp = ++H.z_launches; CUDA_TRY(launch_zsweep_tuned(H.zmaps[b], H.zp[b], H.stream)); }
-    else CUDA_TRY(launch_zsweep_simple(H.D[b], S, H.stream));
-    if (H.stats_on && !first) { CUDA_TRY(launch_stats(H.D[0], H.stats, H.stream)); H.stats_count += 1; }   // rms_add, df.cpp:606
+    const bool accumulate = H.stats_on && !first;                  // rms_add, df.cpp:606
+    if (H.tuned) {
+        H.zp[b].S = S;
+        H.zp[b].stats = accumulate ? H.stats : nullptr;            // N2 fused into the epilogue
+        CUDA_TRY(launch_zsweep_tuned(H.zmaps[b], H.zp[b], H.stream));
+    } else {
+        CUDA_TRY(launch_zsweep_simple(H.D[b], S, H.stream));
+        if (accumulate) CUDA_TRY(launch_stats(H.D[0], H.stats, H.stream));
+    }
+    if (accumulate) H.stats_count += 1;
     CUDA_TRY(cudaEventRecord(H.ev_free[b], H.stream));
     if (H.timing) CUDA_TRY(cudaEventRecord(H.ev[3], H.stream));
     H.step += 1;
@@ -666,13 +694,19 @@ void run_step(dfb_filter_s& H, double dt, bool first) {
     }
 }
 
-const double* field_ptr(const dfb_filter_s& H, int which) {
+const double* field_ptr0(const dfb_filter_s& H, int which) {
     switch (which) {
         case DFB_U_FLUC: return H.D[0].f[0].fluc;   case DFB_V_FLUC: return H.D[0].f[1].fluc;   case DFB_W_FLUC: return H.D[0].f[2].fluc;
         case DFB_T_FLUC: return H.D[0].T_fluc;      case DFB_RHO_FLUC: return H.D[0].rho_fluc;
         case DFB_U_FILT: return H.D[0].f[0].filt_old; case DFB_V_FILT: return H.D[0].f[1].filt_old; case DFB_W_FILT: return H.D[0].f[2].filt_old;
     }
     return nullptr;
+}
+
+// plane p of a batch: the dense arrays are [P][Ny*W]
+const double* field_ptr(const dfb_filter_s& H, int which, int plane = 0) {
+    const double* p = field_ptr0(H, which);
+    return p ? p + (size_t)plane * H.D[0].ps_cells : nullptr;
 }
 
 template <class Fn>
@@ -702,9 +736,10 @@ int dfb_config_init(dfb_config* cfg) {
     return DFB_OK;
 }
 
-int dfb_create(const dfb_config* cfg, dfb_handle* out) {
+static int create_impl(const dfb_config* cfg, int nplanes, dfb_handle* out) {
     if (!cfg || !out) return fail(DFB_ERR_ARG, "cfg/out is NULL");
     *out = nullptr;
+    if (nplanes < 1 || nplanes > DFB_MAXP) return fail(DFB_ERR_ARG, "nplanes must be 1.." + std::to_string(DFB_MAXP));
     if (cfg->struct_bytes != (int)sizeof(dfb_config))
         return fail(DFB_ERR_ARG, "dfb_config.struct_bytes does not match this library (call dfb_config_init first)");
     std::unique_ptr<dfb_filter_s> H(new dfb_filter_s());
@@ -729,6 +764,8 @@ int dfb_create(const dfb_config* cfg, dfb_handle* out) {
         H->kernel_variant = cfg->kernel_variant;
         H->seed = cfg->seed;
         H->plane_id = cfg->plane_id;
+        H->nplanes = nplanes;
+        if (nplanes > 1 && cfg->noise_mode != DFB_NOISE_GENERATE) throw Error{DFB_ERR_ARG, "a batch of planes generates its own noise (noise_mode = DFB_NOISE_GENERATE)"};
         build_plan(*cfg, H->plan);
         if (H->noise_mode == DFB_NOISE_INJECT && (H->plan.k0 != 0 || H->plan.k1 != H->plan.NzG))
             throw Error{DFB_ERR_ARG, "noise injection is defined on the whole plane (k_begin = k_end = 0)"};
@@ -752,6 +789,15 @@ int dfb_create(const dfb_config* cfg, dfb_handle* out) {
     });
     if (rc != DFB_OK) return rc;
     *out = H.release();
+    return DFB_OK;
+}
+
+int dfb_create(const dfb_config* cfg, dfb_handle* out) { return create_impl(cfg, 1, out); }
+int dfb_create_batch(const dfb_config* cfg, int nplanes, dfb_handle* out) { return create_impl(cfg, nplanes, out); }
+
+int dfb_num_planes(dfb_handle h, int* nplanes) {
+    if (!h || !nplanes) return fail(DFB_ERR_ARG, "handle/nplanes is NULL");
+    *nplanes = h->nplanes;
     return DFB_OK;
 }
 
@@ -800,7 +846,9 @@ int dfb_get_table(dfb_handle h, int which, int arg, double* dst, int cap) {
     else if (which == 11) {
         if (arg < 0 || arg > P.coef.Nmax || P.coef.ptr[arg] < 0) return fail(DFB_ERR_ARG, "half-width not present in this plane");
         src = P.coef.vals.data() + P.coef.ptr[arg]; n = 2 * arg + 1;
-    } else return fail(DFB_ERR_ARG, "unknown table selector");
+    } else if (which == 12) { src = P.vert_y.data(); n = P.Ny + 1; }
+    else if (which == 13) { src = P.vert_z.data(); n = P.NzG + 1; }
+    else return fail(DFB_ERR_ARG, "unknown table selector");
     if (cap < n) return fail(DFB_ERR_ARG, "dst too small");
     std::memcpy(dst, src, sizeof(double) * n);
     return DFB_OK;
@@ -829,23 +877,26 @@ int dfb_first_step(dfb_handle h) {   // constructor semantics on demand (inject 
     return guarded([&] { run_step(*h, 0.0, true); });
 }
 
-int dfb_get_field(dfb_handle h, int which, double* dst, int dst_on_device) {
+int dfb_get_field_plane(dfb_handle h, int plane, int which, double* dst, int dst_on_device) {
     if (!h || !dst) return fail(DFB_ERR_ARG, "handle/dst is NULL");
-    const double* src = field_ptr(*h, which);
+    if (plane < 0 || plane >= h->nplanes) return fail(DFB_ERR_ARG, "plane out of range");
+    const double* src = field_ptr(*h, which, plane);
     if (!src) return fail(DFB_ERR_ARG, "unknown field selector");
     return guarded([&] {
         CUDA_TRY(cudaSetDevice(h->device));
-        const size_t bytes = sizeof(double) * (size_t)h->D[0].Ny * h->D[0].W;
+        const size_t bytes = sizeof(double) * h->D[0].ps_cells;
         CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, dst_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
         CUDA_TRY(cudaStreamSynchronize(h->stream));
     });
 }
 
+int dfb_get_field(dfb_handle h, int which, double* dst, int dst_on_device) { return dfb_get_field_plane(h, 0, which, dst, dst_on_device); }
+
 int dfb_filter_to_host(dfb_handle h, double dt, double* u, double* v, double* w, double* T, double* rho) {
     if (!h) return fail(DFB_ERR_ARG, "handle is NULL");
     return guarded([&] {
         run_step(*h, dt, false);
-        const size_t bytes = sizeof(double) * (size_t)h->D[0].Ny * h->D[0].W;
+        const size_t bytes = sizeof(double) * h->D[0].ps_cells * h->nplanes;     // a batch delivers [P][Ny*Nz] per field
         double* dst[5] = {u, v, w, T, rho};
         for (int i = 0; i < 5; ++i)
             if (dst[i]) CUDA_TRY(cudaMemcpyAsync(dst[i], field_ptr(*h, i), bytes, cudaMemcpyDeviceToHost, h->stream));
@@ -858,7 +909,7 @@ int dfb_filter_to_host_begin(dfb_handle h, double dt, double* u, double* v, doub
     return guarded([&] {
         if (h->pipe_begun - h->pipe_ended >= 2) throw Error{DFB_ERR_STATE, "two dfb_filter_to_host_begin calls are already outstanding: call dfb_filter_to_host_end first"};
         CUDA_TRY(cudaSetDevice(h->device));
-        const size_t n = (size_t)h->D[0].Ny * h->D[0].W, bytes = n * sizeof(double);
+        const size_t n = h->D[0].ps_cells * h->nplanes, bytes = n * sizeof(double);
         const int p = (int)(h->pipe_begun & 1);
         if (!h->copy) {
             CUDA_TRY(cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking));
@@ -896,7 +947,7 @@ int dfb_filter_to_host_end(dfb_handle h) {
 int dfb_filter_batch(dfb_handle h, int nsteps, const double* dt, double* out) {
     if (!h || !dt || nsteps < 0) return fail(DFB_ERR_ARG, "bad argument");
     return guarded([&] {
-        const size_t n = (size_t)h->D[0].Ny * h->D[0].W;
+        const size_t n = h->D[0].ps_cells * h->nplanes;
         for (int s = 0; s < nsteps; ++s) {
             run_step(*h, dt[s], false);
             if (out)
@@ -908,13 +959,15 @@ int dfb_filter_batch(dfb_handle h, int nsteps, const double* dt, double* out) {
     });
 }
 
-int dfb_device_ptr(dfb_handle h, int which, void** ptr) {
+int dfb_device_ptr_plane(dfb_handle h, int plane, int which, void** ptr) {
     if (!h || !ptr) return fail(DFB_ERR_ARG, "handle/ptr is NULL");
-    const double* p = field_ptr(*h, which);
+    if (plane < 0 || plane >= h->nplanes) return fail(DFB_ERR_ARG, "plane out of range");
+    const double* p = field_ptr(*h, which, plane);
     if (!p) return fail(DFB_ERR_ARG, "unknown field selector");
     *ptr = const_cast<double*>(p);
     return DFB_OK;
 }
+int dfb_device_ptr(dfb_handle h, int which, void** ptr) { return dfb_device_ptr_plane(h, 0, which, ptr); }
 
 int dfb_scatter_to_cells(dfb_handle h, int which, int n, const int* plane_index, const int* dst_index, const double* mean, double scale,
                          double* dst) {
@@ -941,6 +994,7 @@ int dfb_sync(dfb_handle h) {
 static int set_noise_impl(dfb_handle h, int field, const double* r_ys, const double* left, const double* right, size_t halo_pitch) {
     if (!h || !r_ys || field < 0 || field > 2) return fail(DFB_ERR_ARG, "bad argument");
     if (h->noise_mode != DFB_NOISE_INJECT) return fail(DFB_ERR_STATE, "handle was not created with noise_mode = DFB_NOISE_INJECT");
+    if (h->nplanes != 1) return fail(DFB_ERR_STATE, "noise injection is defined for single-plane handles");
     return guarded([&] {
         CUDA_TRY(cudaSetDevice(h->device));
         const FieldDev& F = h->D[h->step & 1].f[field];      // the set the next step reads
@@ -1006,7 +1060,7 @@ int dfb_get_state(dfb_handle h, double* filt_old3, int64_t* step) {
     if (!h) return fail(DFB_ERR_ARG, "handle is NULL");
     return guarded([&] {
         CUDA_TRY(cudaSetDevice(h->device));
-        const size_t n = (size_t)h->D[0].Ny * h->D[0].W;
+        const size_t n = h->D[0].ps_cells * h->nplanes;                 // [3][P][Ny*Nz]
         if (filt_old3)
             for (int f = 0; f < 3; ++f)
                 CUDA_TRY(cudaMemcpyAsync(filt_old3 + f * n, h->D[0].f[f].filt_old, n * 8, cudaMemcpyDeviceToHost, h->stream));
@@ -1019,7 +1073,7 @@ int dfb_set_state(dfb_handle h, const double* filt_old3, int64_t step) {
     if (!h || step < 0) return fail(DFB_ERR_ARG, "bad argument");
     return guarded([&] {
         CUDA_TRY(cudaSetDevice(h->device));
-        const size_t n = (size_t)h->D[0].Ny * h->D[0].W;
+        const size_t n = h->D[0].ps_cells * h->nplanes;
         if (filt_old3)
             for (int f = 0; f < 3; ++f)
                 CUDA_TRY(cudaMemcpyAsync(h->D[0].f[f].filt_old, filt_old3 + f * n, n * 8, cudaMemcpyHostToDevice, h->stream));
@@ -1077,21 +1131,22 @@ int dfb_stats_enable(dfb_handle h, int on) {
     if (!h) return fail(DFB_ERR_ARG, "handle is NULL");
     return guarded([&] {
         CUDA_TRY(cudaSetDevice(h->device));
-        const size_t n = (size_t)h->D[0].Ny * h->D[0].W;
+        const size_t n = h->D[0].ps_cells * h->nplanes;
         if (on && !h->stats) h->stats = h->dalloc<double>(6 * n);
         if (on) { CUDA_TRY(cudaMemsetAsync(h->stats, 0, 6 * n * sizeof(double), h->stream)); h->stats_count = 0; }
         h->stats_on = on != 0;             // off: keep what was accumulated, stop accumulating
     });
 }
 
-int dfb_stats_get(dfb_handle h, int which, int as_rms, double* dst, int64_t* count) {
+int dfb_stats_get_plane(dfb_handle h, int plane, int which, int as_rms, double* dst, int64_t* count) {
     if (!h || which < 0 || which > 5) return fail(DFB_ERR_ARG, "bad argument");
+    if (plane < 0 || plane >= h->nplanes) return fail(DFB_ERR_ARG, "plane out of range");
     if (!h->stats) return fail(DFB_ERR_STATE, "statistics are not enabled (dfb_stats_enable)");
     return guarded([&] {
         CUDA_TRY(cudaSetDevice(h->device));
-        const size_t n = (size_t)h->D[0].Ny * h->D[0].W;
+        const size_t n = h->D[0].ps_cells;
         if (dst) {
-            CUDA_TRY(cudaMemcpyAsync(dst, h->stats + (size_t)which * n, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            CUDA_TRY(cudaMemcpyAsync(dst, h->stats + ((size_t)plane * 6 + which) * n, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
             CUDA_TRY(cudaStreamSynchronize(h->stream));
             if (as_rms && h->stats_count > 0 && which < 5)
                 for (size_t i = 0; i < n; ++i) dst[i] = std::sqrt(dst[i] / (double)h->stats_count);   // plot_rms, df.cpp:615-620
@@ -1099,6 +1154,7 @@ int dfb_stats_get(dfb_handle h, int which, int as_rms, double* dst, int64_t* cou
         if (count) *count = h->stats_count;
     });
 }
+int dfb_stats_get(dfb_handle h, int which, int as_rms, double* dst, int64_t* count) { return dfb_stats_get_plane(h, 0, which, as_rms, dst, count); }
 
 // write_csv (df.cpp:764-803), opt-in: header, fixed notation with 15 decimals, one row per cell
 int dfb_write_csv(dfb_handle h, const char* path) {
@@ -1124,6 +1180,86 @@ int dfb_write_csv(dfb_handle h, const char* path) {
     });
 }
 
+// write_tecplot (df.cpp:712-762), opt-in.  `file << double << endl` with the stream's default formatting == "%g\n".
+int dfb_write_tecplot(dfb_handle h, const char* path) {
+    if (!h || !path) return fail(DFB_ERR_ARG, "bad argument");
+    return guarded([&] {
+        CUDA_TRY(cudaSetDevice(h->device));
+        const int Ny = h->D[0].Ny, W = h->D[0].W, k0 = h->plan.k0;
+        const size_t n = (size_t)Ny * W;
+        std::vector<double> buf(3 * n);
+        for (int i = 0; i < 3; ++i)
+            CUDA_TRY(cudaMemcpyAsync(buf.data() + (size_t)i * n, field_ptr(*h, i), n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        FILE* fp = std::fopen(path, "w");
+        if (!fp) throw Error{DFB_ERR_IO, std::string("cannot open ") + path + " for writing"};
+        std::fputs("VARIABLES = \"z\", \"y\", \"u_fluc\", \"v_fluc\", \"w_fluc\" \n", fp);                 // df.cpp:715
+        std::fprintf(fp, "ZONE T=\"Flow Field\", I=%d, J=%d, F=BLOCK\n", W + 1, Ny + 1);                  // df.cpp:716
+        std::fputs("VARLOCATION=([3-5]=CELLCENTERED)\n", fp);                                             // df.cpp:717
+        for (int j = 0; j < Ny + 1; ++j) for (int k = 0; k < W + 1; ++k) std::fprintf(fp, "%g\n", h->plan.vert_z[k0 + k]);   // df.cpp:721-726
+        for (int j = 0; j < Ny + 1; ++j) for (int k = 0; k < W + 1; ++k) std::fprintf(fp, "%g\n", h->plan.vert_y[j]);        // df.cpp:729-734
+        for (int f = 0; f < 3; ++f)                                                                        // df.cpp:737-758
+            for (size_t c = 0; c < n; ++c) std::fprintf(fp, "%g\n", buf[(size_t)f * n + c]);
+        std::fclose(fp);
+    });
+}
+
+// get_rms (df.cpp:584-611): reset the sums, `nsteps` steps with accumulation (on the device, in the z-sweep's epilogue)
+int dfb_get_rms(dfb_handle h, int nsteps, double dt) {
+    if (!h || nsteps < 0) return fail(DFB_ERR_ARG, "bad argument");
+    int rc = dfb_stats_enable(h, 1);
+    if (rc != DFB_OK) return rc;
+    return guarded([&] {
+        for (int i = 0; i < nsteps; ++i) run_step(*h, dt, false);
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        h->stats_on = false;                 // the sums stay readable; later dfb_filter calls do not add to them
+    });
+}
+
+// plot_rms (df.cpp:613-675)
+int dfb_write_rms_csv(dfb_handle h, const char* path) {
+    if (!h || !path) return fail(DFB_ERR_ARG, "bad argument");
+    if (!h->stats) return fail(DFB_ERR_STATE, "statistics are not enabled (dfb_stats_enable / dfb_get_rms)");
+    return guarded([&] {
+        CUDA_TRY(cudaSetDevice(h->device));
+        const int Ny = h->D[0].Ny, W = h->D[0].W, k0 = h->plan.k0;
+        const size_t n = (size_t)Ny * W;
+        std::vector<double> buf(5 * n);
+        CUDA_TRY(cudaMemcpyAsync(buf.data(), h->stats, 5 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        const double cnt = (double)std::max<int64_t>(h->stats_count, 1);
+        for (double& v : buf) v = std::sqrt(v / cnt);                                                      // df.cpp:615-621
+        FILE* fp = std::fopen(path, "w");
+        if (!fp) throw Error{DFB_ERR_IO, std::string("cannot open ") + path + " for writing"};
+        std::fputs("z, y, u'_rms, v'_rms, w'_rms, T'_rms, rho'_rms \n", fp);                               // df.cpp:630
+        for (int j = 0; j < Ny; ++j)
+            for (int k = 0; k < W; ++k) {
+                const size_t c = (size_t)j * W + k;
+                std::fprintf(fp, "%g, %g, %g, %g, %g, %g, %g\n", h->plan.vert_z[k0 + k], h->plan.vert_y[j],           // df.cpp:633-639
+                             buf[c], buf[n + c], buf[2 * n + c], buf[3 * n + c], buf[4 * n + c]);
+            }
+        std::fclose(fp);
+    });
+}
+
+// N3: which cell of this handle's slab contains each face centre (us3d_user.f90:85-114 runs over faces; the map is built once)
+int dfb_face_map(dfb_handle h, int n, const double* yf, const double* zf, int* plane_index) {
+    if (!h || n < 0 || (n > 0 && (!yf || !zf || !plane_index))) return fail(DFB_ERR_ARG, "bad argument");
+    const Plan& P = h->plan;
+    const std::vector<double>& vy = P.vert_y;
+    const std::vector<double>& vz = P.vert_z;
+    const int Ny = P.Ny, NzG = P.NzG, W = P.Nz();
+    for (int i = 0; i < n; ++i) {
+        // cell j with vy[j] <= y < vy[j+1], clamped to the plane
+        int j = (int)(std::upper_bound(vy.begin(), vy.end(), yf[i]) - vy.begin()) - 1;
+        int k = (int)(std::upper_bound(vz.begin(), vz.end(), zf[i]) - vz.begin()) - 1;
+        j = std::min(std::max(j, 0), Ny - 1);
+        k = std::min(std::max(k, 0), NzG - 1);
+        plane_index[i] = (k >= P.k0 && k < P.k1) ? j * W + (k - P.k0) : -1;
+    }
+    return DFB_OK;
+}
+
 int dfb_debug_yprof(dfb_handle h, unsigned long long* out8) {
     if (!h || !out8) return fail(DFB_ERR_ARG, "bad argument");
     return guarded([&] {
@@ -1143,18 +1279,6 @@ int dfb_debug_timeline(dfb_handle h, unsigned long long* out512) {
         CUDA_TRY(cudaStreamSynchronize(h->side));
         CUDA_TRY(cudaMemcpy(out512, h->tl, 512 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
         timeline_reset(*h);
-    });
-}
-
-int dfb_debug_ztrace(dfb_handle h, unsigned long long* out, int n) {
-    // development aid (DFB_DEBUG_Z & 64): per-unit clock64 stamps of the warps resident on SM 0
-    if (!h || !out || n > 4096) return fail(DFB_ERR_ARG, "bad argument");
-    return guarded([&] {
-        CUDA_TRY(cudaStreamSynchronize(h->stream));
-        if (!h->zp[0].prof) throw Error{DFB_ERR_STATE, "no profile buffer"};
-        CUDA_TRY(cudaMemcpy(out, h->zp[0].prof, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost));
-        CUDA_TRY(cudaMemset(h->zp[0].prof, 0, sizeof(unsigned long long) * 4096));
-        CUDA_TRY(cudaMemset(h->zp[0].prof + 2048, 0xff, sizeof(unsigned long long) * 256));     // per-SM earliest start (atomicMin)
     });
 }
 

@@ -20,6 +20,7 @@ namespace dfb {
 constexpr int YJ = 8;          // output rows per thread / per row group of the tuned y-sweep
 constexpr int Y_G = 4;         // row groups (consumer warps) per y-sweep tile: 32 output rows share one sample stream
 constexpr int Y_TK = 128;      // columns per y-sweep tile (each lane owns 4 of them)
+constexpr int DFB_MAXP = 16;   // planes one handle can advance in one launch set (dfb_create_batch)
 
 struct FieldDev {
     int Ny_max, Nz_max;
@@ -28,10 +29,11 @@ struct FieldDev {
     int pitch_y;           // doubles
     int pitch_z, zoff;     // doubles
     int yshift;            // extended column x -> r_zs logical column x + yshift
-    double* r_ys;
-    double* r_zs;
-    double* filt_old;
+    double* r_ys;          // plane p of a batch: + p * ps_ys
+    double* r_zs;          //                     + p * ps_zs
+    double* filt_old;      //                     + p * PlaneDev::ps_cells (also fluc, T_fluc, rho_fluc)
     double* fluc;
+    size_t ps_ys, ps_zs;   // doubles per plane of r_ys / r_zs (planes of a batch are stacked along the rows)
     const int* Ny_row;     // [Ny]
     const int* Nz_row;     // [Ny]
     const int* Ny_cell;    // [Ny*NzG] or nullptr (row-uniform)
@@ -44,6 +46,8 @@ constexpr int ROWC = 8;
 
 struct PlaneDev {
     int Ny, W, NzG, k0;
+    int P;                     // planes in this handle (1 unless dfb_create_batch): same geometry and tables, own noise streams and state
+    size_t ps_cells;           // Ny * W
     FieldDev f[3];
     double* T_fluc;
     double* rho_fluc;
@@ -76,8 +80,6 @@ struct StepConsts {
 
 // ---- noise generation work description (one segment = one row of one logical array) ----
 struct NoiseArray {
-    uint64_t state;            // pcg32 state at the first draw of this step's array
-    uint64_t inc;
     const void* seg_jump;      // Jump[n_seg]: jump from `state` to the segment's first pair
     const long long* seg_q0;   // first pair index of each segment (global pair index within the array)
     const int* seg_np;         // pairs in each segment
@@ -89,7 +91,9 @@ struct NoiseArray {
 struct Jump;   // noise.cuh
 
 struct NoiseParams {
-    NoiseArray a[6];
+    NoiseArray a[6];            // geometry of the (up to) six logical arrays, shared by the planes of a batch
+    uint64_t pstate[DFB_MAXP][6];   // per plane and array: pcg32 state at the first draw of this step's array
+    uint64_t pinc[DFB_MAXP][6];     //                      stream increment
     const Jump* slot_jump;      // (A, G) for delta = 4*t: state' = A*state + inc*G
     int n_arrays;
     int max_np;                 // largest segment (pairs)
@@ -118,9 +122,9 @@ struct ZUnit {                     // one row x one strip of 32*zk columns x one
     int j, c0, f;
     int nchunk;                    // tap-loop chunks
     int line0;                     // first line (zk doubles) of the staged window
-    int cbytes;                    // bytes of the padded coefficient vector
-    int coff16;                    // offset of the padded coefficient vector in coef_pad, in units of 16 doubles
-    int flag;                      // index of the (row, strip) completion flag: set by the u unit, awaited by the v unit
+    int cbytes;                    // bytes staged after the window: the padded coefficient vector (direct form) or its 128-byte header (recursive form)
+    int coff16;                    // offset of those bytes in coef_pad, in units of 16 doubles
+    int pad;
 };
 static_assert(sizeof(ZUnit) == 32, "ZUnit is loaded as 8 ints, one per lane");
 struct ZMaps { CUtensorMap m[3]; };   // r_zs[f] as {16 doubles, pitch/16 lines, Ny rows}, 128-byte swizzle
@@ -128,20 +132,20 @@ struct ZMaps { CUtensorMap m[3]; };   // r_zs[f] as {16 doubles, pitch/16 lines,
 struct ZParams {
     PlaneDev D;
     StepConsts S;
-    const ZUnit* units;          // all u units (most expensive first), then all w units, then all v units
-    int n_units;
-    int* flags;                  // [rows x strips]: step stamp written when the u unit of that strip has stored its blended field
-    int stamp;                   // this launch's stamp (step + 1)
+    const ZUnit* units;          // n_uv items of two units (u, v of one (row, strip)), then n_items - n_uv items of one unit (w), each kind most expensive first
+    int n_items, n_uv;           // items per plane; the work counter runs over n_items * D.P (item = c / P, plane = c % P)
     int* counter;                // work counter, zeroed by the y-sweep that precedes this launch
-    const double* coef_pad;      // padded coefficient vectors B_N[m] = b_N[m - 16 - d(N)], zero elsewhere
+    const double* coef_pad;      // padded coefficient vectors B_N[m] = b_N[m - 16 - d(N)], zero elsewhere, + one 128-byte header line each
     const long long* coef_pad_ptr;   // [Nmax+1] offsets (doubles, 16-byte aligned) into coef_pad
+    double* stats;               // N2 running sums [P][6][Ny*W] (u'^2, v'^2, w'^2, T'^2, rho'^2, u'v') accumulated by this launch, or nullptr
     int zk;                      // outputs per lane: 16 (128-byte lines) or 8 (64-byte lines); an item is 32*zk columns
     int box_lines;               // lines per staged window (box height of the tensor maps)
     int box_bytes;               // box_lines * zk * 8
-    int unit_bytes;              // bytes per staging buffer: box_lines*128 + padded coefficient vector, 1024-aligned
+    int unit_bytes;              // bytes per staging buffer: window | parameter line / coefficient vector | row constants | filt_old strip; 1024-aligned
+    int rc_off, fo_off;          // offsets of the row constants (64 B) and of the staged filt_old strip (32 lines) in a staging buffer
     int nblocks;
     int smem_bytes;
-    int n_sm;                    // CTAs are dealt round-robin to the SMs: CTA b sits in residency slot b / n_sm of its SM
+    int n_sm;
     unsigned long long* tl;      // development aid (DFB_TIMELINE), see NoiseParams
     int zmode;                   // 0: direct Toeplitz tap loop; 1: recursive evaluation of the exponential window
     int debug;                   // development probes only (0 in production)

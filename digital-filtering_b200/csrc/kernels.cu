@@ -46,8 +46,9 @@ __device__ __forceinline__ void tl_stamp(unsigned long long* tl, int end) {
 // =================================================================================================
 // H1: white noise
 // =================================================================================================
-__device__ __forceinline__ void noise_block1(const NoiseParams& P, const PlaneDev& D, int slot, int seg, int bz) {
+__device__ __forceinline__ void noise_block1(const NoiseParams& P, const PlaneDev& D, int slot, int seg, int bz, int pl) {
     const NoiseArray& A = P.a[bz];
+    const uint64_t A_state = P.pstate[pl][bz], A_inc = P.pinc[pl][bz];
     if (seg >= A.n_seg) return;
     // all four table reads are requested together (the slot is clamped so that the read is always legal): one memory round trip
     // per thread instead of two dependent ones
@@ -56,10 +57,10 @@ __device__ __forceinline__ void noise_block1(const NoiseParams& P, const PlaneDe
     const Jump tj = P.slot_jump[min(slot, P.max_np - 1)];
     const long long q0 = A.seg_q0[seg];
     if (slot >= np) return;
-    uint64_t s = sj.A * A.state + A.inc * sj.C;
-    s = tj.A * s + A.inc * tj.C;
+    uint64_t s = sj.A * A_state + A_inc * sj.C;
+    s = tj.A * s + A_inc * tj.C;
     double z0, z1;
-    normal_pair(s, A.inc, z0, z1);
+    normal_pair(s, A_inc, z0, z1);
 
     const long long q = q0 + slot;
     const FieldDev& F = D.f[A.field];
@@ -67,7 +68,7 @@ __device__ __forceinline__ void noise_block1(const NoiseParams& P, const PlaneDe
         // r_ys: element e = r*NzG + g, segment = padded row r, g in [xk0, xk0+We)
         const long long rowbase = (long long)seg * D.NzG + F.xk0;
         const long long x0 = 2 * q - rowbase;
-        double* dst = F.r_ys + (size_t)seg * F.pitch_y;
+        double* dst = F.r_ys + (size_t)pl * F.ps_ys + (size_t)seg * F.pitch_y;
         const bool in0 = x0 >= 0 && x0 < F.We, in1 = x0 + 1 >= 0 && x0 + 1 < F.We;
         if (in0 && in1 && ((reinterpret_cast<uintptr_t>(dst + x0) & 15u) == 0)) {
             *reinterpret_cast<double2*>(dst + x0) = make_double2(z0, z1);
@@ -79,7 +80,7 @@ __device__ __forceinline__ void noise_block1(const NoiseParams& P, const PlaneDe
         // r_zs halo: element e = j*2M + h; h < M: global column h-M (left of the plane), else NzG + h-M
         const int M = F.Nz_max;
         const long long e0 = 2 * q - (long long)seg * 2 * M;
-        double* dst = F.r_zs + (size_t)seg * F.pitch_z + F.zoff;
+        double* dst = F.r_zs + (size_t)pl * F.ps_zs + (size_t)seg * F.pitch_z + F.zoff;
         const int Wz = D.W + 2 * M;
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
@@ -92,16 +93,16 @@ __device__ __forceinline__ void noise_block1(const NoiseParams& P, const PlaneDe
     }
 }
 
-__device__ __forceinline__ void noise_block(const NoiseParams& P, const PlaneDev& D, int bx, int seg, int bz) {
+__device__ __forceinline__ void noise_block(const NoiseParams& P, const PlaneDev& D, int bx, int seg, int bz, int pl) {
     constexpr int NU = NOISE_UNROLL;
 #pragma unroll NU
-    for (int r = 0; r < NOISE_PAIRS; ++r) noise_block1(P, D, (bx * NOISE_PAIRS + r) * NOISE_THREADS + threadIdx.x, seg, bz);
+    for (int r = 0; r < NOISE_PAIRS; ++r) noise_block1(P, D, (bx * NOISE_PAIRS + r) * NOISE_THREADS + threadIdx.x, seg, bz, pl);
 }
 
-// one CTA per (NOISE_THREADS x NOISE_PAIRS pairs, segment, array)
+// one CTA per (NOISE_THREADS x NOISE_PAIRS pairs, segment, array x plane of the batch)
 __global__ void __launch_bounds__(NOISE_THREADS) noise_kernel(const NoiseParams P, const PlaneDev D) {
     if (threadIdx.x == 0 && (blockIdx.y & 31) == 0) tl_stamp(P.tl, 0);     // sampled: one row in 32 (same-address atomics)
-    noise_block(P, D, blockIdx.x, blockIdx.y, blockIdx.z);
+    noise_block(P, D, blockIdx.x, blockIdx.y, (int)(blockIdx.z % P.n_arrays), (int)(blockIdx.z / P.n_arrays));
     if (threadIdx.x == 0 && (blockIdx.y & 31) == 0) tl_stamp(P.tl, 1);
 }
 
@@ -111,14 +112,14 @@ __global__ void __launch_bounds__(NOISE_THREADS) noise_kernel(const NoiseParams 
 __global__ void __launch_bounds__(256) ysweep_simple_kernel(const PlaneDev D, int field) {
     const FieldDev& F = D.f[field];
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = blockIdx.y;
+    const int j = blockIdx.y, pl = blockIdx.z;
     if (x >= F.We) return;
     const int N = F.Ny_cell ? F.Ny_cell[(size_t)j * D.NzG + F.xk0 + x] : F.Ny_row[j];
     const double* b = D.coef_vals + D.coef_ptr[N] + N;
-    const double* r = F.r_ys + (size_t)(j + F.Ny_max) * F.pitch_y + x;
+    const double* r = F.r_ys + (size_t)pl * F.ps_ys + (size_t)(j + F.Ny_max) * F.pitch_y + x;
     double sum = 0.0;
     for (int i = -N; i <= N; ++i) sum = fma(b[i], r[(ptrdiff_t)i * F.pitch_y], sum);   // df.cpp:373-375
-    F.r_zs[(size_t)j * F.pitch_z + F.zoff + x + F.yshift] = sum;                        // df.cpp:377
+    F.r_zs[(size_t)pl * F.ps_zs + (size_t)j * F.pitch_z + F.zoff + x + F.yshift] = sum;   // df.cpp:377
 }
 
 struct EpiOut { double u, v, w, T, rho; };
@@ -143,7 +144,7 @@ __device__ __forceinline__ void epilogue_cell(const double* __restrict__ rc, con
 
 __global__ void __launch_bounds__(256) zsweep_epilogue_simple_kernel(const PlaneDev D, const StepConsts S) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = blockIdx.y;
+    const int j = blockIdx.y, pl = blockIdx.z;
     if (k >= D.W) return;
     double z[3];
 #pragma unroll
@@ -151,12 +152,12 @@ __global__ void __launch_bounds__(256) zsweep_epilogue_simple_kernel(const Plane
         const FieldDev& F = D.f[f];
         const int N = F.Nz_cell ? F.Nz_cell[(size_t)j * D.NzG + D.k0 + k] : F.Nz_row[j];
         const double* b = D.coef_vals + D.coef_ptr[N] + N;
-        const double* r = F.r_zs + (size_t)j * F.pitch_z + F.zoff + F.Nz_max + k;
+        const double* r = F.r_zs + (size_t)pl * F.ps_zs + (size_t)j * F.pitch_z + F.zoff + F.Nz_max + k;
         double sum = 0.0;
         for (int i = -N; i <= N; ++i) sum = fma(b[i], r[i], sum);                        // df.cpp:397-399
         z[f] = sum;
     }
-    const size_t idx = (size_t)j * D.W + k;
+    const size_t idx = (size_t)pl * D.ps_cells + (size_t)j * D.W + k;
     EpiOut o;
     double ou, ov, ow;
     epilogue_cell(D.rowc + (size_t)j * ROWC, S, z[0], z[1], z[2],
@@ -233,9 +234,12 @@ __global__ void __launch_bounds__(160, 3) ysweep_tma_kernel(const __grid_constan
     // One tile per CTA (gridDim.x == n_tiles), or a resident grid whose CTAs walk the (longest-first) tile list with a stride:
     // with every CTA resident from the start, the block scheduler has nothing of this kernel pending and lets the next step's
     // noise CTAs (low-priority stream) in beside it.
-    for (int tix = blockIdx.x; tix < P.n_tiles; tix += gridDim.x) {
-    const YTile t = P.tiles[P.tile0 + tix];
+    const int nP = P.D.P;                 // planes of a batch: tile list shared, plane = fastest index (longest-first order kept)
+    for (int tix = blockIdx.x; tix < P.n_tiles * nP; tix += gridDim.x) {
+    const YTile t = P.tiles[P.tile0 + tix / nP];
+    const int pl = tix % nP;
     const FieldDev& F = P.D.f[t.field];
+    const int prow0 = pl * F.rows_y;      // first padded row of this plane in the stacked r_ys
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NS; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], Y_G); }
@@ -268,7 +272,7 @@ __global__ void __launch_bounds__(160, 3) ysweep_tma_kernel(const __grid_constan
 #pragma unroll
                 for (int w = 0; w < Y_G; ++w) if (c >= cs[w] && c < ce[w]) bytes += (uint32_t)(sizeof(double) * RC * YJ);
                 mbar_expect_tx(&sm.full[s], bytes);
-                tma_load_2d(&sm.samples[s][0][0], map, t.col0, c * RC, &sm.full[s]);
+                tma_load_2d(&sm.samples[s][0][0], map, t.col0, prow0 + c * RC, &sm.full[s]);
 #pragma unroll
                 for (int w = 0; w < Y_G; ++w)
                     if (c >= cs[w] && c < ce[w])
@@ -340,7 +344,7 @@ __global__ void __launch_bounds__(160, 3) ysweep_tma_kernel(const __grid_constan
 #pragma unroll
     for (int jj = 0; jj < YJ; ++jj) {
         if (jj >= g.nrows) break;
-        double* dst = F.r_zs + (size_t)(g.j0 + jj) * F.pitch_z + F.zoff + F.yshift;
+        double* dst = F.r_zs + (size_t)pl * F.ps_zs + (size_t)(g.j0 + jj) * F.pitch_z + F.zoff + F.yshift;
 #pragma unroll
         for (int h = 0; h < NC / 2; ++h) {
             const int x = xa0 + 64 * h;
@@ -388,8 +392,11 @@ __global__ void __launch_bounds__(160, 3) ysweep_rec_kernel(const __grid_constan
     static_assert(RC == 8, "the chunk tree folds 8 rows");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     YSmem<RC, NS>& sm = *reinterpret_cast<YSmem<RC, NS>*>(smem_raw);
-    const YTile t = P.tiles[P.tile0 + blockIdx.x];
+    const int nP = P.D.P;
+    const YTile t = P.tiles[P.tile0 + blockIdx.x / nP];
+    const int pl = blockIdx.x % nP;
     const FieldDev& F = P.D.f[t.field];
+    const int prow0 = pl * F.rows_y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
@@ -434,7 +441,7 @@ __global__ void __launch_bounds__(160, 3) ysweep_rec_kernel(const __grid_constan
                     if (need[w]) bytes += (uint32_t)(sizeof(double) * RC * YJ);
                 }
                 mbar_expect_tx(&sm.full[s], bytes);
-                tma_load_2d(&sm.samples[s][0][0], map, t.col0, c * RC, &sm.full[s]);
+                tma_load_2d(&sm.samples[s][0][0], map, t.col0, prow0 + c * RC, &sm.full[s]);
 #pragma unroll
                 for (int w = 0; w < Y_G; ++w)
                     if (need[w])
@@ -529,7 +536,7 @@ __global__ void __launch_bounds__(160, 3) ysweep_rec_kernel(const __grid_constan
     for (int jj = 0; jj < YJ; ++jj) {
         if (jj >= g.nrows) break;
         const double gl = __ldg(gc + jj), gh = __ldg(gc + 8 + jj);
-        double* dst = F.r_zs + (size_t)(g.j0 + jj) * F.pitch_z + F.zoff + F.yshift;
+        double* dst = F.r_zs + (size_t)pl * F.ps_zs + (size_t)(g.j0 + jj) * F.pitch_z + F.zoff + F.yshift;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int x = xa0 + 64 * h;
@@ -549,22 +556,23 @@ __global__ void __launch_bounds__(160, 3) ysweep_rec_kernel(const __grid_constan
 // =================================================================================================
 // H2z + H3 + H4 + H5 tuned: z-sweep for row-uniform half-widths with the fused epilogue.
 //
-// Persistent and warp-independent: every warp is a worker that pulls items (row j, strip of 512
-// columns; most expensive first) from a global counter and runs each item field by field (u, v, w)
-// through a private double-buffered shared-memory window.  One unit = (item, field):
+// Persistent and warp-independent: every warp is a worker that pulls ITEMS from a global counter -- a (row j, strip of
+// 32*ZK columns[, plane of a batch]) as the pair of units u, v run back to back, or as the single unit w; pairs first,
+// most expensive first -- through a private double-buffered shared-memory window.  One unit = (row, strip, field):
 //   * staging: ONE lane issues two TMA operations per unit -- a 3-D cp.async.bulk.tensor box
-//     {16 doubles, 50 x 128-byte lines, 1 row} of r_zs with 128-byte swizzle (lane l's 16 samples of
-//     chunk ch are line l+ch; the swizzle makes the LDS.128 of 8 consecutive lines conflict-free)
-//     and a cp.async.bulk of the row's padded coefficient vector -- both landing on the unit's
-//     mbarrier while the previous unit is still in its tap loop;
-//   * tap loop: lane l owns the 16 consecutive outputs k = c0 + 16 l + (0..15).  Along z every
-//     output of a row shares one coefficient vector, so the loop is a register-blocked Toeplitz
-//     product: per chunk 16 samples + 16 new coefficients (16 LDS.128) feed 256 DFMA.  The window
-//     starts on a 128-byte line; the distance d to the first tap is folded into the padded vector
-//     B[m] = b[m - 16 - d];
-//   * epilogue per field from registers: filt_old prefetched before the tap loop, blend (H3),
-//     Lund scaling (H4; v' uses u's blended value kept in registers), SRA (H5); each of the eight
-//     output arrays is written exactly once with streaming stores.
+//     {ZK doubles, box_lines lines, 1 row} of r_zs with 128/64-byte swizzle (lane l's ZK samples of chunk ch are
+//     line l+ch; the swizzle makes the LDS.128 of 8 consecutive lines conflict-free) and a cp.async.bulk of the
+//     row's parameter line (recursive form) / padded coefficient vector (direct form) -- both landing on the unit's
+//     mbarrier while the previous unit is still computing;
+//   * tap loop: lane l owns the ZK consecutive outputs k = c0 + ZK l + (0..ZK-1); recursive evaluation of the
+//     exponential window (MODE 1) or register-blocked Toeplitz product (MODE 0), see below;
+//   * epilogue per field from registers: filt_old prefetched before the tap loop, blend (H3), Lund scaling (H4),
+//     SRA (H5); each of the eight output arrays is written exactly once.  v' = b u_filt + c v_filt (df.cpp:437)
+//     needs u's blended value: the u unit leaves its strip in a per-warp shared-memory line buffer (lane-owned
+//     layout), the v unit of the same item -- the very next unit of the same warp -- picks it up from there: no
+//     flag, no fence, no second trip through global memory;
+//   * N2 (opt-in): the running sums of u'^2, v'^2, w'^2, T'^2, rho'^2, u'v' (rms_add, df.cpp:571-582) are
+//     accumulated here, where the five values are in registers.
 // =================================================================================================
 // Cell arithmetic of the fused epilogue with every rounding spelled out, so that the result does not
 // depend on which code path (coalesced / direct / partial strip) a cell takes: slabs stay bit-identical
@@ -580,29 +588,38 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
         ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
 }
 
-__device__ __forceinline__ void z_issue_unit(const ZParams& P, const ZMaps& maps, const int* desc, void* buf, uint64_t* bar) {
-    // called by one lane: two TMA operations land the unit's window and coefficient vector on `bar`.
+// Is the strip of a unit handled through the coalesced (piece-major) epilogue?  Whole strip inside the slab and 16-byte aligned.
+__device__ __forceinline__ bool z_strip_coalesced(const ZParams& P, int j, int c0, int plane) {
+    const size_t sbase = (size_t)plane * P.D.ps_cells + (size_t)j * P.D.W + c0;
+    return (c0 + 32 * P.zk <= P.D.W) && ((sbase & 1) == 0) && !(P.debug & 4);
+}
+
+__device__ __forceinline__ void z_issue_unit(const ZParams& P, const ZMaps& maps, const int* desc, int plane, void* buf, uint64_t* bar) {
+    // called by one lane: up to four TMA operations land everything the unit reads on `bar` --
+    //   the window (3-D tensor box of r_zs, swizzled), the row's parameter line / padded coefficient vector,
+    //   the row's eight epilogue constants, and (blend steps, coalesced strips) the strip of filt_old --
+    // so that the warp itself issues no global load at all: nothing of a unit waits on a memory round trip.
     // The buffer was last touched through the generic proxy (tap-loop reads, transpose scratch):
     // order those accesses before the async-proxy writes of the TMA engine.
-    // desc = ZUnit as 8 ints in shared memory: [0] j, [1] c0, [2] f, [3] nchunk, [4] line0, [5] cbytes, [6] coff16, [7] flag
+    // desc = ZUnit as 8 ints in shared memory: [0] j, [1] c0, [2] f, [3] nchunk, [4] line0, [5] cbytes, [6] coff16
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    const int j = desc[0], c0 = desc[1], f = desc[2];
     const uint32_t cbytes = (uint32_t)desc[5];
-    mbar_expect_tx(bar, (uint32_t)P.box_bytes + cbytes);
-    tma_load_3d(buf, &maps.m[desc[2]], 0, desc[4], desc[0], bar);
-    tma_load_1d(reinterpret_cast<unsigned char*>(buf) + P.box_bytes, P.coef_pad + (size_t)desc[6] * 16, cbytes, bar);
+    const bool fo = !P.S.first_step && z_strip_coalesced(P, j, c0, plane);
+    const uint32_t strip_bytes = 32u * (uint32_t)P.zk * 8u;
+    unsigned char* b = reinterpret_cast<unsigned char*>(buf);
+    mbar_expect_tx(bar, (uint32_t)P.box_bytes + cbytes + (uint32_t)(ROWC * sizeof(double)) + (fo ? strip_bytes : 0u));
+    tma_load_3d(b, &maps.m[f], 0, desc[4], plane * P.D.Ny + j, bar);
+    tma_load_1d(b + P.box_bytes, P.coef_pad + (size_t)desc[6] * 16, cbytes, bar);
+    tma_load_1d(b + P.rc_off, P.D.rowc + (size_t)j * ROWC, ROWC * sizeof(double), bar);
+    if (fo) tma_load_1d(b + P.fo_off, P.D.f[f].filt_old + (size_t)plane * P.D.ps_cells + (size_t)j * P.D.W + c0, strip_bytes, bar);
 }
 
-__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
-    int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-
-template <int ZK, int MODE>
+template <int ZK, int MODE, bool STATS>
 __global__ void __maxnreg__(MODE == 1 ? Z_REC_MAXNREG : 168) zsweep_epilogue_kernel(const __grid_constant__ ZMaps maps, const ZParams P) {
-    constexpr int Z_STRIP = 32 * ZK;         // columns per unit
     constexpr int LB = ZK * 8;               // bytes per staged line (= one lane's ZK samples): 128 -> SWIZZLE_128B, 64 -> SWIZZLE_64B
     constexpr int PPL = ZK / 2;              // 16-byte pieces per line
+    constexpr int UB = 32 * LB;              // bytes of the per-warp u line buffer
     // hardware swizzle of the TMA box: the 16-byte piece index is XORed with address bits [7:9] (128B mode) or [7:8] (64B mode)
     auto swz = [](int line) { return ZK == 16 ? (line & 7) : ((line >> 1) & 3); };
     extern __shared__ __align__(1024) unsigned char zsm_unaligned[];
@@ -610,86 +627,74 @@ __global__ void __maxnreg__(MODE == 1 ? Z_REC_MAXNREG : 168) zsweep_epilogue_ker
     unsigned char* zsm_raw = zsm_unaligned + ((1024u - (smem_u32(zsm_unaligned) & 1023u)) & 1023u);
     const PlaneDev& D = P.D;
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-    // per warp: 2 buffers of unit_bytes (window lines + coefficient vector); then 2 mbarriers and 2 unit descriptors per warp
-    unsigned char* wbase = zsm_raw + (size_t)warp * 2 * P.unit_bytes;
-    unsigned char* tail = zsm_raw + (size_t)4 * 2 * P.unit_bytes;
+    // per warp: 2 staging buffers of unit_bytes (window lines + parameter line / coefficient vector) + the u line buffer;
+    // then 2 mbarriers and 2 item descriptors (3 units x 8 ints) per warp
+    const size_t wbytes = (size_t)2 * P.unit_bytes + UB;
+    unsigned char* wbase = zsm_raw + (size_t)warp * wbytes;
+    unsigned char* ubuf = wbase + (size_t)2 * P.unit_bytes;
+    unsigned char* tail = zsm_raw + (size_t)4 * wbytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(tail) + warp * 2;
-    int* descs = reinterpret_cast<int*>(tail + 64) + warp * 16;              // [2][8]
+    int* descs = reinterpret_cast<int*>(tail + 64) + warp * 32;              // [2 items][<= 2 units][8]
     if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
     // Programmatic dependent launch: this CTA became resident while the y-sweep's last tiles were still running;
-    // wait for that grid to complete (and its writes to r_zs to be visible) before the first unit is claimed/staged.
+    // wait for that grid to complete (and its writes to r_zs to be visible) before the first item is claimed/staged.
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
     if (lane == 0) tl_stamp(P.tl, 0);
     const long long tstart = (P.debug & 16) ? clock64() : 0;
-    int trace_slot = -1;                                   // development aid (DFB_DEBUG_Z & 64): unit timeline of the warps on SM 0
-    unsigned smid = 0;
-    if (P.debug & 64) {
-        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        if (lane == 0) {
-            unsigned long long gt;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-            atomicMin(P.prof + 2048 + smid, gt);
-        }
-        if (smid == 0) {
-            int sl = 0;
-            if (lane == 0) sl = (int)atomicAdd(P.prof + 8, 1ull);
-            trace_slot = __shfl_sync(0xffffffffu, sl, 0);
-            if (trace_slot >= 15) trace_slot = -1;
-            if (trace_slot >= 0 && lane == 0) P.prof[16 + trace_slot * 256 + 255] = (unsigned long long)warp;
-        }
-    }
-    // claim the first two units; stage the first
+    // Items: first the (u, v) pairs -- two units back to back, v picks u's blended strip up from the warp's line buffer --, then the w
+    // units as items of their own (the queue's tail is then one unit long, not three).  Item it of a plane: units [off, off + nun).
+    const int nP = D.P, n_total = P.n_items * nP;
+    auto item_units = [&](int g) { return (g / nP) < P.n_uv ? 2 : 1; };
+    auto item_off = [&](int g) { const int it = g / nP; return it < P.n_uv ? 2 * it : P.n_uv + it; };
+    auto fetch_item = [&](int g) {                          // the item's unit descriptors, one int per lane (16 or 8 lanes)
+        return lane < 8 * item_units(g) ? __ldg(reinterpret_cast<const int*>(P.units + item_off(g)) + lane) : 0;
+    };
+    // claim the first two items; stage the first unit
     int claim = 0;
     if (lane == 0) claim = atomicAdd(P.counter, 1);
-    int cur = __shfl_sync(0xffffffffu, claim, 0);
-    if (cur >= P.n_units) return;
-    if (lane < 8) descs[lane] = reinterpret_cast<const int*>(P.units + cur)[lane];
+    int itemA = __shfl_sync(0xffffffffu, claim, 0);
+    if (itemA >= n_total) return;
+    if (lane < 16) descs[lane] = fetch_item(itemA);
     if (lane == 0) claim = atomicAdd(P.counter, 1);
-    int nxt = __shfl_sync(0xffffffffu, claim, 0);
-    if (nxt < P.n_units && lane < 8) descs[8 + lane] = reinterpret_cast<const int*>(P.units + nxt)[lane];
+    int itemB = __shfl_sync(0xffffffffu, claim, 0);
+    if (itemB < n_total && lane < 16) descs[16 + lane] = fetch_item(itemB);
     __syncwarp();
-    if (lane == 0) z_issue_unit(P, maps, descs, wbase, &bars[0]);
+    if (lane == 0) z_issue_unit(P, maps, descs, itemA % nP, wbase, &bars[0]);
 
-    // Pipeline per unit n (buffer n & 1, barrier phase (n >> 1) & 1):
-    //   top:    stage unit n+1 (its descriptor is already in shared memory), claim unit n+2 (atomic, result not awaited)
+    // Pipeline per unit n (buffer n & 1, barrier phase (n >> 1) & 1); an item is the three consecutive units u, v, w:
+    //   top:    stage unit n+1 (the v unit of this pair, or the first unit of the next item, whose descriptors are already in shared
+    //           memory); at an item's first unit also claim the item after the next (atomic, result not awaited)
     //   middle: tap loop of unit n
-    //   bottom: epilogue of unit n; fetch the descriptor of unit n+2 into the slot unit n just vacated
+    //   bottom: epilogue of unit n; at an item's last unit fetch the descriptors of the newly claimed item into the slot just vacated
+    int slot = 0, phase = 0;
     for (int n = 0;; ++n) {
-        const int* dcur = descs + (n & 1) * 8;
-        int* dnext = descs + ((n + 1) & 1) * 8;
-        const bool have_next = nxt < P.n_units;
+        const int* dcur = descs + slot * 16 + phase * 8;
+        const bool last_phase = phase == item_units(itemA) - 1;
+        const bool have_next = !last_phase || itemB < n_total;
         if (have_next && lane == 0) {
             unsigned char* nb = wbase + (size_t)((n + 1) & 1) * P.unit_bytes;
-            z_issue_unit(P, maps, dnext, nb, &bars[(n + 1) & 1]);
+            const int* dnext = last_phase ? descs + (slot ^ 1) * 16 : dcur + 8;
+            z_issue_unit(P, maps, dnext, (last_phase ? itemB : itemA) % nP, nb, &bars[(n + 1) & 1]);
         }
-        if (have_next && lane == 0) claim = atomicAdd(P.counter, 1);        // unit n+2
+        if (phase == 0 && itemB < n_total && lane == 0) claim = atomicAdd(P.counter, 1);        // the item after the next
 
         const int j = dcur[0], c0 = dcur[1], f = dcur[2];
         const int nchunk = __shfl_sync(0xffffffffu, dcur[3], 0);
-        const int flag_idx = dcur[7];
         const int k0 = c0 + lane * ZK;
         const bool active = k0 < D.W;
-        const size_t base = (size_t)j * D.W + k0;
-        const size_t sbase = (size_t)j * D.W + c0;                            // first cell of the warp's strip
-        // whole strip inside the plane and 16-byte aligned: go through the shared-memory transpose (coalesced global access)
-        const bool coalesced = (c0 + Z_STRIP <= D.W) && ((sbase & 1) == 0) && !(P.debug & 4);
+        const size_t pbase = (size_t)(itemA % nP) * D.ps_cells;                // this plane's share of the dense output arrays
+        const size_t base = pbase + (size_t)j * D.W + k0;
+        const size_t sbase = pbase + (size_t)j * D.W + c0;                    // first cell of the warp's strip
+        // whole strip inside the plane and 16-byte aligned: piece-major epilogue (coalesced global access); its filt_old strip was
+        // staged with the window
+        const bool coalesced = z_strip_coalesced(P, j, c0, itemA % nP);
         const FieldDev& F = D.f[f];
         const bool blend = !P.S.first_step;
-        const long long tunit = (P.debug & (16 | 64)) ? clock64() : 0;
-
-        // filt_old of this strip, coalesced (piece p = lane + 32 m): requested now, consumed after the tap loop
-        double2 fo_pc[ZK / 2];
-        auto request_fo = [&]() {
-            if (blend && coalesced) {
-#pragma unroll
-                for (int m = 0; m < ZK / 2; ++m) fo_pc[m] = __ldcs(reinterpret_cast<const double2*>(F.filt_old + sbase) + lane + 32 * m);
-            }
-        };
-        request_fo();
+        const long long tunit = (P.debug & 16) ? clock64() : 0;
         const long long t0 = (P.debug & 16) ? clock64() : 0;
         mbar_wait(&bars[n & 1], (n >> 1) & 1);
-        const long long t1 = (P.debug & (16 | 64)) ? clock64() : 0;
+        const long long t1 = (P.debug & 16) ? clock64() : 0;
         unsigned char* cbuf = wbase + (size_t)(n & 1) * P.unit_bytes;
         const double* B = reinterpret_cast<const double*>(cbuf + P.box_bytes);
         double acc[ZK];
@@ -849,145 +854,110 @@ __global__ void __maxnreg__(MODE == 1 ? Z_REC_MAXNREG : 168) zsweep_epilogue_ker
         }
         }
         __syncwarp();                    // every lane is done with this buffer's window: it becomes the transpose scratch
-        // descriptor of unit n+2 (claimed at the top of this unit): request it now, store it after the epilogue
-        int nn = P.n_units, dreg = 0;
-        if (have_next) {
-            nn = __shfl_sync(0xffffffffu, claim, 0);
-            if (nn < P.n_units && lane < 8) dreg = __ldg(reinterpret_cast<const int*>(P.units + nn) + lane);
+        // descriptors of the item claimed at this item's first unit: request them now, store them after the epilogue
+        int itemC = n_total, dreg = 0;
+        if (last_phase && itemB < n_total) {
+            itemC = __shfl_sync(0xffffffffu, claim, 0);
+            if (itemC < n_total) dreg = fetch_item(itemC);
         }
-        const long long t2 = (P.debug & (16 | 64)) ? clock64() : 0;
+        const long long t2 = (P.debug & 16) ? clock64() : 0;
 
         // ---- epilogue of this (strip, field) ----
         {
-            const double* rcp = D.rowc + (size_t)j * ROWC;
-            const double rc_own = __ldg(rcp + (f == 0 ? 0 : (f == 1 ? 2 : 3)));
+            const double* rc = reinterpret_cast<const double*>(cbuf + P.rc_off);        // the row's constants, staged with the window
+            const double rc_own = rc[f == 0 ? 0 : (f == 1 ? 2 : 3)];
+            const double rc0 = rc[0], rc1 = rc[1], rc4 = rc[4], rc5 = rc[5], rc6 = rc[6];
             const double sa = P.S.sa[f], sb = P.S.sb[f];
-            if (f == 1) {
-                // v' = b u_filt + c v_filt (df.cpp:437): u's blended field of this strip comes from the u unit
-                // (queued far ahead of every v unit); wait for its stamp, then read it like any other global data
-                if (lane == 0) {
-                    while (ld_acquire_gpu(P.flags + flag_idx) != P.stamp) __nanosleep(100);
-                }
-                __syncwarp();
-            }
+            double* stats = (STATS && blend) ? P.stats + (size_t)(itemA % nP) * 6 * D.ps_cells + ((size_t)j * D.W) : nullptr;
             if (coalesced) {
-                // Lane l owns line l (its ZK cells) of a 32-line scratch tile; global memory wants piece
-                // p = lane + 32 m.  Both views are conflict-free under the same XOR swizzle.
-                const int own = lane * LB, osw = swz(lane) << 4;
-                auto put_pieces = [&](const double2* v) {      // piece-major registers -> tile
-#pragma unroll
-                    for (int m = 0; m < ZK / 2; ++m) {
-                        const int pc_ = lane + 32 * m, r = pc_ / PPL;
-                        *reinterpret_cast<double2*>(cbuf + r * LB + ((((pc_ % PPL) ^ swz(r))) << 4)) = v[m];
-                    }
-                };
-                auto get_pieces = [&](double2* v) {            // tile -> piece-major registers
-#pragma unroll
-                    for (int m = 0; m < ZK / 2; ++m) {
-                        const int pc_ = lane + 32 * m, r = pc_ / PPL;
-                        v[m] = *reinterpret_cast<const double2*>(cbuf + r * LB + ((((pc_ % PPL) ^ swz(r))) << 4));
-                    }
-                };
-                auto put_own = [&](const double* v) {          // this lane's ZK cells -> its line
+                // One transpose per unit: lane l owns line l (its ZK cells) of a 32-line tile; global memory wants 16-byte piece
+                // p = lane + 32 m of the strip.  The tap loop's results go through the (swizzled, conflict-free both ways) tile once;
+                // everything after is elementwise with per-row constants, so it is done in piece order: filt_old pieces come from the
+                // staged strip, every output piece goes straight to its coalesced global address, and u's blended pieces wait for
+                // the v unit in the warp's line buffer.
+                {
+                    const int own = lane * LB, osw = swz(lane) << 4;
 #pragma unroll
                     for (int i = 0; i < ZK / 2; ++i)
-                        *reinterpret_cast<double2*>(cbuf + own + ((i << 4) ^ osw)) = make_double2(v[2 * i], v[2 * i + 1]);
+                        *reinterpret_cast<double2*>(cbuf + own + ((i << 4) ^ osw)) = make_double2(acc[2 * i], acc[2 * i + 1]);
+                }
+                __syncwarp();
+                const double2* fo_t = reinterpret_cast<const double2*>(cbuf + P.fo_off);
+                double2* ub = reinterpret_cast<double2*>(ubuf);
+                double2* g_fo = reinterpret_cast<double2*>(F.filt_old + sbase);
+                double2* g_fl = reinterpret_cast<double2*>(F.fluc + sbase);
+                double2* g_T = reinterpret_cast<double2*>(D.T_fluc + sbase);
+                double2* g_r = reinterpret_cast<double2*>(D.rho_fluc + sbase);
+                auto add2 = [&](int which, int pc, double2 x, double2 y) {              // sums[which] += x * y (mul, then add: df.cpp:575-579)
+                    double2* gs = reinterpret_cast<double2*>(stats + (size_t)which * D.ps_cells + c0) + pc;
+                    const double2 cur = *gs;
+                    *gs = make_double2(__dadd_rn(cur.x, __dmul_rn(x.x, y.x)), __dadd_rn(cur.y, __dmul_rn(x.y, y.y)));
                 };
-                auto get_own = [&](double* v) {
 #pragma unroll
-                    for (int i = 0; i < ZK / 2; ++i) {
-                        const double2 t = *reinterpret_cast<const double2*>(cbuf + own + ((i << 4) ^ osw));
-                        v[2 * i] = t.x; v[2 * i + 1] = t.y;
+                for (int m = 0; m < ZK / 2; ++m) {
+                    const int pc = lane + 32 * m, r = pc / PPL;
+                    double2 z = *reinterpret_cast<const double2*>(cbuf + r * LB + ((((pc % PPL) ^ swz(r))) << 4));
+                    if (blend) {                                                                 // correlate_fields, df.cpp:415
+                        const double2 fo = fo_t[pc];
+                        z.x = epi_blend(fo.x, sa, z.x, sb); z.y = epi_blend(fo.y, sa, z.y, sb);
                     }
-                };
-                auto load_strip = [&](const double* gstrip, double* v) {     // coalesced global read -> this lane's cells
-                    double2 pc[ZK / 2];
-#pragma unroll
-                    for (int m = 0; m < ZK / 2; ++m) pc[m] = __ldcg(reinterpret_cast<const double2*>(gstrip) + lane + 32 * m);
-                    put_pieces(pc);
-                    __syncwarp();
-                    get_own(v);
-                    __syncwarp();
-                };
-                auto store_strip = [&](double* gstrip, const double* v, bool streaming) {
-                    double2 pc[ZK / 2];
-                    put_own(v);
-                    __syncwarp();
-                    get_pieces(pc);
-                    __syncwarp();
-#pragma unroll
-                    for (int m = 0; m < ZK / 2; ++m) {
-                        double2* dst = reinterpret_cast<double2*>(gstrip) + lane + 32 * m;
-                        if (streaming) __stcs(dst, pc[m]); else *dst = pc[m];
+                    g_fo[pc] = z;                                                                // filt_old <- filt, df.cpp:440-442
+                    if (f == 0) ub[pc] = z;                                                      // for the v unit that follows
+                    double2 o = make_double2(epi_scale(rc_own, z.x), epi_scale(rc_own, z.y));    // df.cpp:436,438; v.filt term of 437
+                    if (f == 1) {
+                        const double2 uf = ub[pc];
+                        o.x = epi_cross(rc1, uf.x, o.x); o.y = epi_cross(rc1, uf.y, o.y);        // df.cpp:437
+                        if (STATS && stats) add2(5, pc, make_double2(epi_scale(rc0, uf.x), epi_scale(rc0, uf.y)), o);   // u' of the same cells
                     }
-                };
-                double z[ZK];
-                if (blend) {
-                    double fo[ZK];
-                    put_pieces(fo_pc);
-                    __syncwarp();
-                    get_own(fo);
-                    __syncwarp();
-#pragma unroll
-                    for (int i = 0; i < ZK; ++i) z[i] = epi_blend(fo[i], sa, acc[i], sb);      // correlate_fields, df.cpp:415
-                } else {
-#pragma unroll
-                    for (int i = 0; i < ZK; ++i) z[i] = acc[i];
+                    __stcs(g_fl + pc, o);
+                    if (STATS && stats) add2(f, pc, o, o);
+                    if (f == 0 && blend) {                                                       // get_rho_T_fluc, df.cpp:474-481
+                        const double2 t2 = make_double2(__dmul_rn(rc4, o.x), __dmul_rn(rc4, o.y));
+                        const double2 Tv = make_double2(__dmul_rn(t2.x, rc5), __dmul_rn(t2.y, rc5));
+                        const double2 rv = make_double2(__dmul_rn(-t2.x, rc6), __dmul_rn(-t2.y, rc6));
+                        __stcs(g_T + pc, Tv);
+                        __stcs(g_r + pc, rv);
+                        if (STATS && stats) { add2(3, pc, Tv, Tv); add2(4, pc, rv, rv); }
+                    }
                 }
-                store_strip(F.filt_old + sbase, z, false);                                      // filt_old <- filt, df.cpp:440-442
-                double o[ZK];
+            } else {
+                // partial / unaligned strip: every lane walks its own cells in global memory; u's strip waits in the line buffer in
+                // lane-owned layout (both units of a pair take the same path)
+                double* ul = reinterpret_cast<double*>(ubuf) + lane * ZK;
+                if (active) {
+                    double* __restrict__ fold = F.filt_old + base;
+                    double* __restrict__ fluc = F.fluc + base;
+                    double* st = stats ? stats + k0 : nullptr;
 #pragma unroll
-                for (int i = 0; i < ZK; ++i) o[i] = epi_scale(rc_own, z[i]);                    // df.cpp:436,438; v.filt term of 437
-                if (f == 1) {
-                    const double rc1 = __ldg(rcp + 1);
-                    double uf[ZK];
-                    load_strip(D.f[0].filt_old + sbase, uf);
-#pragma unroll
-                    for (int i = 0; i < ZK; ++i) o[i] = epi_cross(rc1, uf[i], o[i]);            // df.cpp:437
-                }
-                store_strip(F.fluc + sbase, o, true);
-                if (f == 0 && blend) {                                                          // get_rho_T_fluc, df.cpp:474-481
-                    const double rc4 = __ldg(rcp + 4), rc5 = __ldg(rcp + 5), rc6 = __ldg(rcp + 6);
-                    double t[ZK];
-#pragma unroll
-                    for (int i = 0; i < ZK; ++i) { z[i] = __dmul_rn(rc4, o[i]); t[i] = __dmul_rn(z[i], rc5); }
-                    store_strip(D.T_fluc + sbase, t, true);
-#pragma unroll
-                    for (int i = 0; i < ZK; ++i) t[i] = __dmul_rn(-z[i], rc6);
-                    store_strip(D.rho_fluc + sbase, t, true);
-                }
-            } else if (active) {
-                double* __restrict__ fold = F.filt_old + base;
-                double* __restrict__ fluc = F.fluc + base;
-                const double* __restrict__ ufp = D.f[0].filt_old + base;
-                const double rc1 = __ldg(rcp + 1), rc4 = __ldg(rcp + 4), rc5 = __ldg(rcp + 5), rc6 = __ldg(rcp + 6);
-#pragma unroll
-                for (int i = 0; i < ZK; ++i) {
-                    if (k0 + i < D.W) {
-                        double za = acc[i];
-                        if (blend) za = epi_blend(fold[i], sa, za, sb);
-                        fold[i] = za;
-                        double oa = epi_scale(rc_own, za);
-                        if (f == 1) oa = epi_cross(rc1, __ldcg(ufp + i), oa);
-                        fluc[i] = oa;
-                        if (f == 0 && blend) {
-                            const double ta = __dmul_rn(rc4, oa);
-                            D.T_fluc[base + i] = __dmul_rn(ta, rc5);
-                            D.rho_fluc[base + i] = __dmul_rn(-ta, rc6);
+                    for (int i = 0; i < ZK; ++i) {
+                        if (k0 + i < D.W) {
+                            double za = acc[i];
+                            if (blend) za = epi_blend(fold[i], sa, za, sb);
+                            fold[i] = za;
+                            if (f == 0) ul[i] = za;
+                            double oa = epi_scale(rc_own, za);
+                            double ufv = 0.0;
+                            if (f == 1) { ufv = ul[i]; oa = epi_cross(rc1, ufv, oa); }
+                            fluc[i] = oa;
+                            if (STATS && st) {
+                                st[(size_t)f * D.ps_cells + i] = __dadd_rn(st[(size_t)f * D.ps_cells + i], __dmul_rn(oa, oa));
+                                if (f == 1) st[(size_t)5 * D.ps_cells + i] = __dadd_rn(st[(size_t)5 * D.ps_cells + i], __dmul_rn(epi_scale(rc0, ufv), oa));
+                            }
+                            if (f == 0 && blend) {
+                                const double ta = __dmul_rn(rc4, oa);
+                                const double Tv = __dmul_rn(ta, rc5), rv = __dmul_rn(-ta, rc6);
+                                D.T_fluc[base + i] = Tv;
+                                D.rho_fluc[base + i] = rv;
+                                if (STATS && st) {
+                                    st[(size_t)3 * D.ps_cells + i] = __dadd_rn(st[(size_t)3 * D.ps_cells + i], __dmul_rn(Tv, Tv));
+                                    st[(size_t)4 * D.ps_cells + i] = __dadd_rn(st[(size_t)4 * D.ps_cells + i], __dmul_rn(rv, rv));
+                                }
+                            }
                         }
                     }
                 }
             }
-            if (f == 0) {
-                __threadfence();          // publish: this strip's blended u field is in global memory
-                __syncwarp();
-                if (lane == 0) *reinterpret_cast<volatile int*>(P.flags + flag_idx) = P.stamp;
-            }
-            __syncwarp();                // scratch reads are done before the buffer is refilled by the next-but-one unit
-        }
-        if (trace_slot >= 0 && lane == 0 && n < 63) {
-            unsigned long long* tr = P.prof + 16 + trace_slot * 256 + 4 * n;
-            tr[0] = (unsigned long long)tunit; tr[1] = (unsigned long long)t1; tr[2] = (unsigned long long)t2; tr[3] = (unsigned long long)clock64();
+            __syncwarp();                // tile / staged-strip reads are done before the buffer is refilled by the next-but-one unit
         }
         if ((P.debug & 16) && lane == 0) {
             const long long t3 = clock64();
@@ -999,12 +969,6 @@ __global__ void __maxnreg__(MODE == 1 ? Z_REC_MAXNREG : 168) zsweep_epilogue_ker
         }
         if (!have_next) {
             if (lane == 0) tl_stamp(P.tl, 1);
-            if ((P.debug & 64) && lane == 0) {
-                unsigned long long gt;
-                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-                atomicMax(P.prof + 2304 + smid, gt);
-                atomicAdd(P.prof + 2560 + smid, (unsigned long long)(n + 1));
-            }
             if ((P.debug & 16) && lane == 0) {
                 const unsigned long long life = (unsigned long long)(clock64() - tstart);
                 atomicAdd(P.prof + 5, life);
@@ -1013,27 +977,33 @@ __global__ void __maxnreg__(MODE == 1 ? Z_REC_MAXNREG : 168) zsweep_epilogue_ker
             }
             break;
         }
-        // descriptor of unit n+2 into the slot unit n just vacated
-        int* dfree = descs + (n & 1) * 8;
-        if (nn < P.n_units && lane < 8) dfree[lane] = dreg;
-        __syncwarp();
-        nxt = nn;
+        if (last_phase) {
+            // descriptors of the newly claimed item into the slot this item just vacated
+            if (itemC < n_total && lane < 16) descs[slot * 16 + lane] = dreg;
+            __syncwarp();
+            itemA = itemB; itemB = itemC; slot ^= 1; phase = 0;
+        } else {
+            ++phase;
+        }
     }
 }
 
 // =================================================================================================
 // N2: running sums of squares (rms_add, df.cpp:571-582) + u'v', opt-in.  mul then add, like the reference.
+// Separate kernel for the general (one-thread-per-cell) path only; the tuned z-sweep accumulates in its epilogue.
 // =================================================================================================
 __global__ void __launch_bounds__(256) stats_kernel(const PlaneDev D, double* __restrict__ sums, size_t n) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;       // cell within the plane
+    if (c >= n) return;
+    const size_t i = (size_t)blockIdx.y * n + c;                          // cell within the batch's dense arrays
+    double* s = sums + (size_t)blockIdx.y * 6 * n + c;                    // [P][6][n]
     const double u = D.f[0].fluc[i], v = D.f[1].fluc[i], w = D.f[2].fluc[i], T = D.T_fluc[i], r = D.rho_fluc[i];
-    sums[i] = __dadd_rn(sums[i], __dmul_rn(u, u));
-    sums[n + i] = __dadd_rn(sums[n + i], __dmul_rn(v, v));
-    sums[2 * n + i] = __dadd_rn(sums[2 * n + i], __dmul_rn(w, w));
-    sums[3 * n + i] = __dadd_rn(sums[3 * n + i], __dmul_rn(T, T));
-    sums[4 * n + i] = __dadd_rn(sums[4 * n + i], __dmul_rn(r, r));
-    sums[5 * n + i] = __dadd_rn(sums[5 * n + i], __dmul_rn(u, v));
+    s[0] = __dadd_rn(s[0], __dmul_rn(u, u));
+    s[n] = __dadd_rn(s[n], __dmul_rn(v, v));
+    s[2 * n] = __dadd_rn(s[2 * n], __dmul_rn(w, w));
+    s[3 * n] = __dadd_rn(s[3 * n], __dmul_rn(T, T));
+    s[4 * n] = __dadd_rn(s[4 * n], __dmul_rn(r, r));
+    s[5 * n] = __dadd_rn(s[5 * n], __dmul_rn(u, v));
 }
 
 // N3: CFD hand-off (ghost cell = mean + fluctuation, the loop a US3D-style plugin runs over its inflow faces, us3d_user.f90:88-113)
@@ -1042,9 +1012,11 @@ __global__ void __launch_bounds__(256) scatter_kernel(const double* __restrict__
                                                       double* __restrict__ dst) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const int c = plane_index[i];
+    if (c < 0) return;                       // face in another rank's slab (dfb_face_map)
     const int d = dst_index[i];
     const double base = mean ? mean[i] : dst[d];
-    dst[d] = __fma_rn(scale, field[plane_index[i]], base);
+    dst[d] = __fma_rn(scale, field[c], base);
 }
 
 cudaError_t launch_scatter(const double* field, int n, const int* plane_index, const int* dst_index, const double* mean, double scale,
@@ -1056,7 +1028,7 @@ cudaError_t launch_scatter(const double* field, int n, const int* plane_index, c
 
 cudaError_t launch_stats(const PlaneDev& D, double* sums, cudaStream_t st) {
     const size_t n = (size_t)D.Ny * D.W;
-    stats_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(D, sums, n);
+    stats_kernel<<<dim3((unsigned)((n + 255) / 256), (unsigned)D.P), 256, 0, st>>>(D, sums, n);
     return cudaGetLastError();
 }
 
@@ -1083,21 +1055,21 @@ cudaError_t launch_noise(const NoiseParams& P, const PlaneDev& D, cudaStream_t s
     if (P.n_arrays == 0) return cudaSuccess;
     int max_seg = 0;
     for (int a = 0; a < P.n_arrays; ++a) max_seg = P.a[a].n_seg > max_seg ? P.a[a].n_seg : max_seg;
-    dim3 grid((unsigned)P.chunks, (unsigned)max_seg, (unsigned)P.n_arrays);
+    dim3 grid((unsigned)P.chunks, (unsigned)max_seg, (unsigned)(P.n_arrays * D.P));
     noise_kernel<<<grid, NOISE_THREADS, 0, st>>>(P, D);
     return cudaGetLastError();
 }
 
 cudaError_t launch_ysweep_simple(const PlaneDev& D, cudaStream_t st) {
     for (int f = 0; f < 3; ++f) {
-        dim3 grid((unsigned)((D.f[f].We + 255) / 256), (unsigned)D.Ny);
+        dim3 grid((unsigned)((D.f[f].We + 255) / 256), (unsigned)D.Ny, (unsigned)D.P);
         ysweep_simple_kernel<<<grid, 256, 0, st>>>(D, f);
     }
     return cudaGetLastError();
 }
 
 cudaError_t launch_zsweep_simple(const PlaneDev& D, const StepConsts& S, cudaStream_t st) {
-    dim3 grid((unsigned)((D.W + 255) / 256), (unsigned)D.Ny);
+    dim3 grid((unsigned)((D.W + 255) / 256), (unsigned)D.Ny, (unsigned)D.P);
     zsweep_epilogue_simple_kernel<<<grid, 256, 0, st>>>(D, S);
     return cudaGetLastError();
 }
@@ -1149,7 +1121,8 @@ cudaError_t launch_ysweep_tma(const YMaps& maps, const YParams& P, int n_dense, 
     if (n_dense > 0) {
         Q.tile0 = 0;
         Q.n_tiles = n_dense;
-        const int grid = P.resident_grid > 0 ? (n_dense < P.resident_grid ? n_dense : P.resident_grid) : n_dense;
+        const int n_all = n_dense * P.D.P;
+        const int grid = P.resident_grid > 0 ? (n_all < P.resident_grid ? n_all : P.resident_grid) : n_all;
         cudaError_t e;
         if (P.tk == 64) {
             cudaLaunchConfig_t cfg = pdl_config((unsigned)grid, 160, sizeof(YSmem<Y_RC, Y_NS, 64>), st, &attr);
@@ -1162,31 +1135,37 @@ cudaError_t launch_ysweep_tma(const YMaps& maps, const YParams& P, int n_dense, 
     }
     if (n_rec > 0) {
         Q.tile0 = n_dense;
-        cudaLaunchConfig_t cfg = pdl_config((unsigned)n_rec, 160, sizeof(YSmem<Y_RC, Y_NS>), st, &attr);
+        cudaLaunchConfig_t cfg = pdl_config((unsigned)(n_rec * P.D.P), 160, sizeof(YSmem<Y_RC, Y_NS>), st, &attr);
         return cudaLaunchKernelEx(&cfg, ysweep_rec_kernel<Y_RC, Y_NS>, maps, Q);
     }
     return cudaSuccess;
 }
 
-static const void* zsweep_fn(int zk, int mode) {
-    if (zk == 16) return mode == 1 ? (const void*)zsweep_epilogue_kernel<16, 1> : (const void*)zsweep_epilogue_kernel<16, 0>;
-    return mode == 1 ? (const void*)zsweep_epilogue_kernel<8, 1> : (const void*)zsweep_epilogue_kernel<8, 0>;
+static const void* zsweep_fn(int zk, int mode, bool stats) {
+    if (stats) {
+        if (zk == 16) return mode == 1 ? (const void*)zsweep_epilogue_kernel<16, 1, true> : (const void*)zsweep_epilogue_kernel<16, 0, true>;
+        return mode == 1 ? (const void*)zsweep_epilogue_kernel<8, 1, true> : (const void*)zsweep_epilogue_kernel<8, 0, true>;
+    }
+    if (zk == 16) return mode == 1 ? (const void*)zsweep_epilogue_kernel<16, 1, false> : (const void*)zsweep_epilogue_kernel<16, 0, false>;
+    return mode == 1 ? (const void*)zsweep_epilogue_kernel<8, 1, false> : (const void*)zsweep_epilogue_kernel<8, 0, false>;
 }
 
 cudaError_t zsweep_prepare(int zk, int mode, size_t smem, int* blocks_per_sm) {
-    const void* fn = zsweep_fn(zk, mode);
-    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, fn, 128, smem);
+    for (int st = 1; st >= 0; --st) {
+        const void* fn = zsweep_fn(zk, mode, st != 0);
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, zsweep_fn(zk, mode, false), 128, smem);
 }
 
 cudaError_t launch_zsweep_tuned(const ZMaps& maps, const ZParams& P, cudaStream_t st) {
     cudaLaunchAttribute attr;
     cudaLaunchConfig_t cfg = pdl_config((unsigned)P.nblocks, 128, (size_t)P.smem_bytes, st, &attr);
     void* args[2] = {const_cast<ZMaps*>(&maps), const_cast<ZParams*>(&P)};
-    return cudaLaunchKernelExC(&cfg, zsweep_fn(P.zk, P.zmode), args);
+    return cudaLaunchKernelExC(&cfg, zsweep_fn(P.zk, P.zmode, P.stats != nullptr), args);
 }
 
 cudaError_t launch_dfma_peak(double* out, int blocks, int iters, cudaStream_t st) {

@@ -37,6 +37,7 @@ struct Plan {
     double u_tau = 0, tau_w = 0;
     std::vector<double> yc_row, dy_row;          // first column of the geometry (ydline*d_i, df.cpp:115-116)
     std::vector<double> csv_yc, csv_zc;          // cell-centre coordinates as write_csv prints them (df.cpp:785-786): [Ny], [NzG]
+    std::vector<double> vert_y, vert_z;          // vertex coordinates y[j*(Nz+1)+k], z[...] of df.cpp:99-100 (uniform in the other index): [Ny+1], [NzG+1]
     std::vector<double> rows;                    // [8][Ny] R11,R21,R22,R33,Us,Ts,rhos,Ms
     FieldPlan f[3];
     CoefTable coef;

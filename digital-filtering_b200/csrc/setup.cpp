@@ -237,25 +237,39 @@ void build_plan(const dfb_config& cfg, Plan& P) {
         P.dy_row[j] = dy.empty() ? 0.0 : dy[(size_t)j * gstride];
     }
 
-    // ---- cell-centre coordinates for the opt-in CSV writer (write_csv, df.cpp:776-786) ----
+    // ---- coordinates for the opt-in writers: vertices (write_tecplot / plot_rms print y[], z[], df.cpp:99-100) and the
+    //      cell centres write_csv derives from them (df.cpp:776-786) ----
+    P.vert_y.resize(Ny + 1); P.vert_z.resize(NzG + 1);
     P.csv_yc.resize(Ny); P.csv_zc.resize(NzG);
     if (default_grid) {
-        // the reference averages the four corner vertices; y = the tanh grid, z[...] = k * 0.000133 (df.cpp:99-100)
-        std::vector<double> yv(561);
-        double y_max = 3 * d_i, a = 2.0;
-        for (int j = 560; j >= 0; --j) {
-            double eta = ((j) * y_max / (560 + 1)) / y_max;
-            yv[std::abs(j - 560)] = y_max * (1 - std::tanh(a * eta) / std::tanh(a));
+        // the reference's vertex grid: y = the tanh stretching, z = k * 0.000133 (df.cpp:92-100); cell centre = mean of the four corners
+        const int Ny0 = 560;
+        const double y_max = 3 * d_i, a = 2.0;
+        std::vector<double> yv(Ny0 + 1);
+        for (int j = Ny0; j >= 0; --j) {
+            const double eta = ((j) * y_max / (Ny0 + 1)) / y_max;
+            yv[std::abs(j - Ny0)] = y_max * (1 - std::tanh(a * eta) / std::tanh(a));
         }
+        for (int j = 0; j <= Ny; ++j) P.vert_y[j] = yv[j];
+        for (int k = 0; k <= NzG; ++k) P.vert_z[k] = k * 0.000133;
         for (int j = 0; j < Ny; ++j) P.csv_yc[j] = 0.25 * (yv[j] + yv[j] + yv[j + 1] + yv[j + 1]);        // df.cpp:785 (n00,n01,n10,n11)
         for (int k = 0; k < NzG; ++k) P.csv_zc[k] = 0.25 * (k * 0.000133 + (k + 1) * 0.000133 + k * 0.000133 + (k + 1) * 0.000133);   // df.cpp:786
     } else {
-        for (int j = 0; j < Ny; ++j) P.csv_yc[j] = yc.empty() ? 0.0 : yc[(size_t)j * gstride];
+        // caller-supplied geometry: vertices from the centres and cell sizes of the first column / first row
+        for (int j = 0; j < Ny; ++j) {
+            const double c = yc.empty() ? (double)j + 0.5 : yc[(size_t)j * gstride];
+            const double hgt = dy.empty() ? 1.0 : dy[(size_t)j * gstride];
+            P.csv_yc[j] = yc.empty() ? 0.0 : c;
+            P.vert_y[j] = c - 0.5 * hgt;
+            if (j == Ny - 1) P.vert_y[Ny] = c + 0.5 * hgt;
+        }
         double zacc = 0.0;
         for (int k = 0; k < NzG; ++k) {
             const double w = dz.empty() ? 1.0 : (per_row ? dz[0] : dz[k]);
+            P.vert_z[k] = zacc;
             P.csv_zc[k] = zacc + 0.5 * w; zacc += w;
         }
+        P.vert_z[NzG] = zacc;
     }
 
     // ---- slab ----

@@ -95,6 +95,15 @@ int dfb_config_init(dfb_config* cfg);
 /* DIGITAL_FILTER::DIGITAL_FILTER(DFConfig) df.cpp:4-66: setup + first step (no blend, T'/rho' = 0). */
 int dfb_create(const dfb_config* cfg, dfb_handle* out);
 int dfb_destroy(dfb_handle h);
+/* BASELINE config 5 -- `nplanes` (1..16) independent planes of ONE geometry advanced by one handle: one launch set per step for all of
+ * them (plane index = an extra tile / work-item coordinate; coefficient tables, band matrices and row constants shared), where one
+ * handle per plane pays three launches per plane.  Plane p draws from RNG stream group cfg->plane_id + p, so it reproduces the
+ * single-plane handle created with that plane_id bit for bit.  Every per-field array of a batch handle is [nplanes][Ny*Nz]:
+ * dfb_filter_to_host fills nplanes*Ny*Nz doubles per pointer, dfb_get_state / dfb_set_state move [3][nplanes][Ny*Nz].
+ * The us3d_user.f90-style caller (my_user_init once, my_user_main_pre every step: us3d_user.f90:21-48, 51-130) creates the batch once
+ * and calls dfb_filter every step; fortran/digital_filtering.f90 exposes it as create_digital_filter_batch. */
+int dfb_create_batch(const dfb_config* cfg, int nplanes, dfb_handle* out);
+int dfb_num_planes(dfb_handle h, int* nplanes);
 
 /* plane size as the reference ends up with it (Ny trimmed, df.cpp:282-288); Nz is this handle's slab width */
 int dfb_dims(dfb_handle h, int* Ny, int* Nz);
@@ -104,7 +113,8 @@ int dfb_dims(dfb_handle h, int* Ny, int* Nz);
  * 8 / 9 y-sweep tiles evaluated recursively / with dense band matrices */
 int dfb_info(dfb_handle h, int what, int field, int64_t* out64);
 /* host copies of the setup tables (for parity tests): which = 0..7 rows R11,R21,R22,R33,Us,Ts,rhos,Ms [Ny];
- * 8 yc row [Ny]; 9 dy row [Ny]; 10 Lt[3]; 11 coefficients of half-width `arg` [2*arg+1] */
+ * 8 yc row [Ny]; 9 dy row [Ny]; 10 Lt[3]; 11 coefficients of half-width `arg` [2*arg+1];
+ * 12 y of the vertex rows [Ny+1]; 13 z of the vertex columns [Nz_global+1] (df.cpp:99-100: the y / z the writers print) */
 int dfb_get_table(dfb_handle h, int which, int arg, double* dst, int cap);
 /* N_y / N_z of field f (dir 0 = y, 1 = z) for the local slab, [Ny*Nz] */
 int dfb_get_half_widths(dfb_handle h, int field, int dir, int* dst);
@@ -129,8 +139,11 @@ int dfb_filter_batch(dfb_handle h, int nsteps, const double* dt, double* out);
 
 /* copies one field (Ny*Nz doubles) to dst; dst_on_device != 0 -> dst is a device pointer */
 int dfb_get_field(dfb_handle h, int which, double* dst, int dst_on_device);
+/* the same for plane `plane` of a batch handle (dfb_get_field = plane 0) */
+int dfb_get_field_plane(dfb_handle h, int plane, int which, double* dst, int dst_on_device);
 /* device pointer to a field, valid until dfb_destroy (for GPU-resident CFD codes / NCCL gathers) */
 int dfb_device_ptr(dfb_handle h, int which, void** ptr);
+int dfb_device_ptr_plane(dfb_handle h, int plane, int which, void** ptr);
 /* the handle's cudaStream_t */
 int dfb_stream(dfb_handle h, void** stream);
 /* CFD hand-off on the device (the call a US3D-style plugin makes per inflow face, us3d_user.f90:88-113:
@@ -162,9 +175,26 @@ int dfb_set_state(dfb_handle h, const double* filt_old3, int64_t step);
  * like plot_rms, not for u'v') and returns the number of accumulated steps. */
 int dfb_stats_enable(dfb_handle h, int on);
 int dfb_stats_get(dfb_handle h, int which, int as_rms, double* dst, int64_t* count);
+int dfb_stats_get_plane(dfb_handle h, int plane, int which, int as_rms, double* dst, int64_t* count);
+/* get_rms (df.cpp:584-611), what the reference's own driver calls (test/cpp-main.cpp:17): reset the sums, run `nsteps` filter(dt)
+ * steps (the reference: 500 steps of dt = 1e-5) accumulating on the device.  Results through dfb_stats_get(.., as_rms = 1, ..)
+ * and dfb_write_rms_csv. */
+int dfb_get_rms(dfb_handle h, int nsteps, double dt);
+/* plot_rms (df.cpp:613-675): "z, y, u'_rms, v'_rms, w'_rms, T'_rms, rho'_rms " then one row per cell with the cell's lower-left VERTEX
+ * coordinates (z[iidx], y[iidx]), default stream formatting (6 significant digits), ", " separators */
+int dfb_write_rms_csv(dfb_handle h, const char* path);
 /* N4 -- write_csv (df.cpp:764-803), opt-in and never called by dfb_filter: "z,y,u_fluc,v_fluc,w_fluc,T_fluc,rho_fluc",
  * fixed notation, 15 decimals, one row per cell in j-major order. */
 int dfb_write_csv(dfb_handle h, const char* path);
+/* write_tecplot (df.cpp:712-762): VARIABLES / ZONE (I = Nz+1, J = Ny+1, F=BLOCK) / VARLOCATION header, then the vertex z and y
+ * blocks ((Ny+1)*(Nz+1) values, one per line) and the cell-centred u', v', w' blocks (Ny*Nz values each), default stream formatting.
+ * (The reference's writer does not compile at HEAD -- member z is undeclared, SURVEY section 0 -- this follows its text.) */
+int dfb_write_tecplot(dfb_handle h, const char* path);
+/* N3 -- face -> (j,k) map for the CFD hand-off (us3d_user.f90:85-114: a plugin loops over its inflow faces j1..j2 and writes ghost cell
+ * ii = ife(j,2)): for n face centres (yf[i], zf[i]) in the plane's coordinates, plane_index[i] = j*Nz + k of the cell of THIS handle's
+ * slab that contains the point (clamped to the nearest cell in y and z), or -1 when the face lies in another rank's slab.  Host arrays;
+ * the result is what dfb_scatter_to_cells takes as plane_index (after a copy to the device). */
+int dfb_face_map(dfb_handle h, int n, const double* yf, const double* zf, int* plane_index);
 
 /* CUDA-event time of the last dfb_filter, ms: stage 0 noise, 1 y-sweep, 2 z-sweep+epilogue, 3 whole step.
  * Only recorded when enabled with dfb_set_timing(h, 1). */

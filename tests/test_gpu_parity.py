@@ -748,3 +748,163 @@ def test_rewind_by_two_steps_is_bit_reproducible(dfb, W):
         a.set_state(None, step + 2)             # filt_old3 = NULL: only the counter moves; prefetch for step 6 restarts
         a.filter(1e-7)
     a.close(); b.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE config 5: batched planes behind one handle; the remaining "next" rows (Tecplot / rms writers, face map)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(72, 530, 20, 16), (64, 130, 16, 12)])
+def test_config5_batch_equals_independent_handles_bitwise(dfb, W, shape):
+    """dfb_create_batch: P planes of one geometry advanced by ONE launch set per step (plane = extra tile / item coordinate) give,
+    plane by plane, exactly what P single-plane handles with plane_id + p give -- every output field, several steps, checkpoint
+    included."""
+    plane = W.plane_profile(*shape)
+    P = 5
+    batch = dfb.DIGITAL_FILTER(dfb.DFConfig.from_plane(plane, seed=9, plane_id=3), nplanes=P)
+    singles = [dfb.DIGITAL_FILTER(dfb.DFConfig.from_plane(plane, seed=9, plane_id=3 + p), fetch=False) for p in range(P)]
+    sel = (dfb.U_FLUC, dfb.V_FLUC, dfb.W_FLUC, dfb.T_FLUC, dfb.RHO_FLUC, dfb.U_FILT, dfb.V_FILT, dfb.W_FILT)
+    for s, dt in enumerate([None, 1e-7, 3e-7, 1e-7]):
+        if dt is not None:
+            batch.filter(dt)
+            for d in singles:
+                d.filter(dt)
+        for p in range(P):
+            for w in sel:
+                assert np.array_equal(batch.get(w, plane=p), singles[p].get(w)), (s, p, w)
+    fo, step = batch.get_state()
+    assert fo.shape == (3, P, plane["Ny"], plane["Nz"]) and step == 4
+    for p in range(P):
+        assert np.array_equal(fo[:, p], singles[p].get_state()[0])
+    # the five fields of all planes in one call: [P][Ny*Nz] per pointer
+    import ctypes as C
+    n = plane["Ny"] * plane["Nz"]
+    host = [np.zeros((P, n)) for _ in range(5)]
+    dfb._check(dfb.lib().dfb_filter_to_host(batch._h, 2e-7, *[h.ctypes.data_as(C.c_void_p) for h in host]))
+    for p, d in enumerate(singles):
+        d.filter(2e-7)
+        for i, w in enumerate(sel[:5]):
+            assert np.array_equal(host[i][p].reshape(plane["Ny"], plane["Nz"]), d.get(w)), (p, w)
+    batch.close()
+    for d in singles:
+        d.close()
+
+
+def test_config5_batch_statistics_per_plane(dfb, W):
+    plane = W.plane_profile(40, 96, 8, 6)
+    batch = dfb.DIGITAL_FILTER(dfb.DFConfig.from_plane(plane, seed=4), nplanes=3)
+    batch.stats_enable(True)
+    acc = np.zeros((3, 6, 40, 96))
+    for _ in range(4):
+        batch.filter(3e-7)
+        for p in range(3):
+            f = [batch.get(w, plane=p) for w in (dfb.U_FLUC, dfb.V_FLUC, dfb.W_FLUC, dfb.T_FLUC, dfb.RHO_FLUC)]
+            for i in range(5):
+                acc[p, i] += f[i] * f[i]
+            acc[p, 5] += f[0] * f[1]
+    for p in range(3):
+        for i in range(6):
+            got, cnt = batch.stats(i, plane=p)
+            assert cnt == 4 and np.array_equal(got, acc[p, i]), (p, i)
+    batch.close()
+
+
+@pytest.mark.parametrize("shape", [(40, 96, 8, 6), (24, 700, 8, 40)])
+def test_N2_fused_statistics_every_path(dfb, W, shape):
+    """the sums accumulated inside the z-sweep's epilogue (tuned kernels: coalesced strips, partial last strip, both lane widths)
+    and by the separate kernel of the general path are the host accumulation of the fetched fields, bit for bit."""
+    plane = W.plane_profile(*shape)
+    for variant in (0, 1):
+        df = dfb.DIGITAL_FILTER(dfb.DFConfig.from_plane(plane, seed=4, kernel_variant=variant))
+        df.stats_enable(True)
+        acc = np.zeros((6,) + df.u.fluc.shape)
+        for _ in range(3):
+            df.filter(3e-7)
+            f = [df.u.fluc, df.v.fluc, df.w.fluc, df.T_fluc, df.rho_fluc]
+            for i in range(5):
+                acc[i] += f[i] * f[i]
+            acc[5] += f[0] * f[1]
+        for i in range(6):
+            got, cnt = df.stats(i)
+            assert cnt == 3 and np.array_equal(got, acc[i]), (variant, i)
+        df.close()
+
+
+def test_get_rms_and_its_csv(dfb, W, tmp_path):
+    """get_rms / plot_rms (df.cpp:584-675): N steps of dt accumulated on the device, then the rms file in the reference's format."""
+    plane = W.plane_profile(40, 96, 8, 6)
+    df = dfb.DIGITAL_FILTER(dfb.DFConfig.from_plane(plane, seed=5))
+    twin = dfb.DIGITAL_FILTER(dfb.DFConfig.from_plane(plane, seed=5))
+    path = tmp_path / "rms.csv"
+    df.get_rms(nsteps=20, dt=1e-5, path=path)
+    acc = np.zeros((5, 40, 96))
+    for _ in range(20):
+        twin.filter(1e-5)
+        for i, a in enumerate((twin.u.fluc, twin.v.fluc, twin.w.fluc, twin.T_fluc, twin.rho_fluc)):
+            acc[i] += a * a
+    rms = np.sqrt(acc / 20)
+    got, cnt = df.stats(0, rms=True)
+    assert cnt == 20 and np.array_equal(got, rms[0])
+    lines = open(path).read().splitlines()
+    assert lines[0] == "z, y, u'_rms, v'_rms, w'_rms, T'_rms, rho'_rms " and len(lines) == 1 + 40 * 96
+    vy, vz = df.table(12, n=41), df.table(13, n=97)
+    for c in (0, 95, 96, 40 * 96 - 1):
+        j, k = divmod(c, 96)
+        want = ", ".join("%g" % x for x in (vz[k], vy[j], rms[0, j, k], rms[1, j, k], rms[2, j, k], rms[3, j, k], rms[4, j, k]))
+        assert lines[1 + c] == want, (c, lines[1 + c], want)
+    # later filter() calls do not add to the sums (get_rms is a self-contained driver)
+    df.filter(1e-5)
+    assert df.stats(0)[1] == 20
+    df.close(); twin.close()
+
+
+def test_N4_tecplot_block_writer(dfb, W, tmp_path):
+    """write_tecplot (df.cpp:712-762): three header lines, vertex z and y blocks of (Ny+1)(Nz+1) values, cell-centred u', v', w' blocks."""
+    plane = W.plane_profile(20, 36, 8, 6)
+    df = dfb.DIGITAL_FILTER(dfb.DFConfig.from_plane(plane, seed=6))
+    df.filter(1e-7)
+    path = tmp_path / "fluc.dat"
+    df.write_tecplot(path)
+    lines = open(path).read().splitlines()
+    assert lines[0] == 'VARIABLES = "z", "y", "u_fluc", "v_fluc", "w_fluc" '
+    assert lines[1] == 'ZONE T="Flow Field", I=37, J=21, F=BLOCK' and lines[2] == "VARLOCATION=([3-5]=CELLCENTERED)"
+    nv, nc = 21 * 37, 20 * 36
+    assert len(lines) == 3 + 2 * nv + 3 * nc
+    vy, vz = df.table(12, n=21), df.table(13, n=37)
+    body = lines[3:]
+    assert body[:37] == ["%g" % z for z in vz] and body[nv:nv + 37] == ["%g" % vy[0]] * 37 and body[2 * nv - 1] == "%g" % vy[20]
+    for f, a in enumerate((df.u.fluc, df.v.fluc, df.w.fluc)):
+        blk = body[2 * nv + f * nc:2 * nv + (f + 1) * nc]
+        assert blk == ["%g" % x for x in a.ravel()], f
+    df.close()
+
+
+def test_N3_face_map_and_scatter_through_it(dfb, W):
+    """face -> (j,k) map (the index a US3D-style plugin needs per inflow face, us3d_user.f90:85-114) on two slabs: every face is
+    claimed by exactly one slab, lands in the cell that contains it, and the scatter through the map fills the ghost cells."""
+    import torch
+    plane = W.plane_profile(40, 96, 8, 6)
+    rng = np.random.default_rng(3)
+    whole = dfb.DIGITAL_FILTER(dfb.DFConfig.from_plane(plane, seed=31))
+    vy, vz = whole.table(12, n=41), whole.table(13, n=97)
+    nf = 500
+    jj, kk = rng.integers(0, 40, nf), rng.integers(0, 96, nf)
+    yf = vy[jj] + (vy[jj + 1] - vy[jj]) * rng.uniform(0.05, 0.95, nf)
+    zf = vz[kk] + (vz[kk + 1] - vz[kk]) * rng.uniform(0.05, 0.95, nf)
+    assert np.array_equal(whole.face_map(yf, zf), jj * 96 + kk)
+    whole.filter(1e-7)
+    ghost = torch.zeros(nf, dtype=torch.float64, device="cuda")
+    claimed = np.zeros(nf, dtype=int)
+    for k0, k1 in [(0, 48), (48, 96)]:
+        part = dfb.DIGITAL_FILTER(dfb.DFConfig.from_plane(plane, seed=31, k_begin=k0, k_end=k1))
+        part.filter(1e-7)
+        m = part.face_map(yf, zf)
+        mine = (kk >= k0) & (kk < k1)
+        assert np.array_equal(m[mine], jj[mine] * (k1 - k0) + kk[mine] - k0) and np.all(m[~mine] == -1)
+        claimed += (m >= 0)
+        part.scatter_to_cells(dfb.U_FLUC, torch.from_numpy(m).cuda(), torch.arange(nf, dtype=torch.int32, device="cuda"), ghost,
+                              mean=torch.zeros(nf, dtype=torch.float64, device="cuda"))
+        part.sync()
+        part.close()
+    assert np.all(claimed == 1)
+    assert np.array_equal(ghost.cpu().numpy(), whole.u.fluc[jj, kk])
+    whole.close()

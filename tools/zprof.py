@@ -1,6 +1,7 @@
 import ctypes, os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
+os.environ.setdefault("DFB_DEBUG_Z", "16")
 import _dfb_import, digital_filtering_b200 as dfb
 from digital_filtering_b200 import workloads as W
 name = sys.argv[1] if len(sys.argv) > 1 else "1024x2048_saturated_N128"
