@@ -39,7 +39,7 @@ struct NoiseHost {            // one logical array of the noise contract
     int field, kind;
     uint64_t inc, state0, npairs;
     int n_seg;
-    void *d_jump = nullptr, *d_q0 = nullptr, *d_np = nullptr;
+    void *d_jump = nullptr, *d_off = nullptr, *d_np = nullptr;
 };
 
 }  // namespace
@@ -78,6 +78,8 @@ struct dfb_filter_s {
     YParams yp[2]{};
     int n_items = 0;
     int n_tiles_dense = 0, n_tiles_rec = 0;   // y-sweep tiles: dense band-matrix tiles first, then recursive tiles
+    YRMaps rmaps[2]{};                        // run-recursive y-sweep (the default form): tensor maps of r_ys with its box
+    int y_form = 0;                           // 0 dense band matrices, 1 chunk-recursive (ysweep_rec_kernel), 2 run-recursive (ysweep_run_kernel)
     // tuned z-sweep
     ZParams zp[2]{};
     ZMaps zmaps[2]{};
@@ -394,6 +396,72 @@ void build_device(dfb_filter_s& H) {
         H.yp[0].prof = H.dalloc<unsigned long long>(8);
         if (std::getenv("DFB_TIMELINE")) { H.tl = H.dalloc<unsigned long long>(512); timeline_reset(H); }
         H.yp[0].debug = std::getenv("DFB_DEBUG_Y") ? std::atoi(std::getenv("DFB_DEBUG_Y")) : 0;
+        H.y_form = yrec_on ? 1 : 0;
+        {
+            // Run-recursive form (ysweep_run_kernel, the default): rows cut into groups of <= YJ consecutive rows of ONE half-width,
+            // never across a block of RB rows; a block x 32 columns = one tile whose whole window is staged in shared memory.
+            // RB = 128 when two such windows fit (fewest re-reads of the overlapping windows), else 64, else 32.
+            cudaDeviceProp prop;
+            CUDA_TRY(cudaGetDeviceProperties(&prop, H.device));
+            bool use_run = false;
+            std::vector<YRGroup> rg;
+            std::vector<YRTile> rt;
+            int wrows_max = 0;
+            for (int RB : {128, 64, 32}) {
+                rg.clear(); rt.clear(); wrows_max = 0;
+                for (int f = 0; f < 3; ++f) {
+                    const FieldPlan& FP = P.f[f];
+                    for (int jb = 0; jb < Ny; jb += RB) {
+                        const int je = std::min(Ny, jb + RB);
+                        std::vector<YRGroup> blk;
+                        for (int j0 = jb; j0 < je;) {
+                            const int N = FP.N_y_row[j0];
+                            int R = 1;
+                            while (j0 + R < je && R < YJ && FP.N_y_row[j0 + R] == N) ++R;
+                            YRGroup g{};
+                            g.j0 = j0; g.nrows = R; g.N = N;
+                            if (N >= 1) {
+                                const long double a = (long double)std::exp(-2.0 * 3.14159265358979323846 * 1.0 / N);
+                                g.a = (double)a;
+                                g.a4 = (double)(a * a * a * a);
+                                g.naN1 = -(double)std::pow(a, (long double)(N + 1));
+                            }
+                            g.inv_s = *P.coef.centre(N);
+                            blk.push_back(g);
+                            j0 += R;
+                        }
+                        std::stable_sort(blk.begin(), blk.end(), [](const YRGroup& x, const YRGroup& y) { return 2 * x.N + 4 * x.nrows > 2 * y.N + 4 * y.nrows; });
+                        YRTile t{};
+                        t.field = f; t.g0 = (int)rg.size(); t.ngroups = (int)blk.size();
+                        int lo = 1 << 30, hi = -1;
+                        for (const YRGroup& g : blk) {
+                            lo = std::min(lo, g.j0 + FP.Ny_max - g.N);
+                            hi = std::max(hi, g.j0 + g.nrows - 1 + FP.Ny_max + g.N);
+                        }
+                        t.wlo = lo; t.wrows = hi - lo + 1;
+                        wrows_max = std::max(wrows_max, round_up(t.wrows, YR_BOX));
+                        rg.insert(rg.end(), blk.begin(), blk.end());
+                        for (int c0 = 0; c0 < D.f[f].We; c0 += YR_C) { t.col0 = c0; rt.push_back(t); }
+                    }
+                }
+                if (ysweep_run_smem(wrows_max) <= (size_t)prop.sharedMemPerBlockOptin) { use_run = true; break; }
+            }
+            // windows that do not fit even with 32-row blocks (N_y beyond ~190): the band-matrix kernels stream them
+            if (const char* ym = std::getenv("DFB_Y_MODE")) use_run = std::atoi(ym) == 2 && use_run;
+            if (use_run) {
+                // most expensive tiles first; the persistent CTAs take them round-robin
+                auto cost = [&](const YRTile& t) { long long c = 0; for (int g = 0; g < t.ngroups; ++g) c += 2 * rg[t.g0 + g].N + 4 * rg[t.g0 + g].nrows + 8; return c; };
+                std::stable_sort(rt.begin(), rt.end(), [&](const YRTile& x, const YRTile& y) { return cost(x) > cost(y); });
+                H.y_form = 2;
+                H.yp[0].rgroups = H.upload(rg);
+                H.yp[0].rtiles = H.upload(rt);
+                H.yp[0].n_rtiles = (int)rt.size();
+                H.yp[0].r_wrows = wrows_max;
+                H.yp[0].r_smem = (int)ysweep_run_smem(wrows_max);
+                H.yp[0].r_grid = prop.multiProcessorCount;
+                CUDA_TRY(ysweep_run_prepare((size_t)H.yp[0].r_smem));
+            }
+        }
         H.yp[1] = H.yp[0];
         H.yp[1].D = H.D[1];
         H.n_items = (int)tiles.size();
@@ -409,6 +477,19 @@ void build_device(dfb_filter_s& H) {
                                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) throw Error{DFB_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")"};
         }
+        if (H.y_form == 2)
+            for (int b = 0; b < 2; ++b)
+                for (int f = 0; f < 3; ++f) {
+                    const FieldDev& F = H.D[b].f[f];
+                    cuuint64_t dims[2] = {(cuuint64_t)F.We, (cuuint64_t)F.rows_y * (cuuint64_t)NP};
+                    cuuint64_t strides[1] = {(cuuint64_t)F.pitch_y * sizeof(double)};
+                    cuuint32_t box[2] = {(cuuint32_t)YR_C, (cuuint32_t)YR_BOX};
+                    cuuint32_t estr[2] = {1u, 1u};
+                    CUresult r = encode_tiled()(&H.rmaps[b].m[f], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, F.r_ys, dims, strides, box, estr,
+                                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    if (r != CUDA_SUCCESS) throw Error{DFB_ERR_CUDA, "cuTensorMapEncodeTiled (y, run form) failed (" + std::to_string((int)r) + ")"};
+                }
         CUDA_TRY(ysweep_prepare());
         ZParams& Z = H.zp[0];
         Z.D = H.D[0];
@@ -559,14 +640,14 @@ void build_device(dfb_filter_s& H) {
             A.inc = (stream << 1) | 1u;
             A.state0 = pcg_lcg(H.seed + A.inc, A.inc);
             std::vector<Jump> jumps;
-            std::vector<long long> q0;
+            std::vector<int> offv;         // r_ys: extended column of the segment's first pair (0 or -1); halo: 0
             std::vector<int> npv;
             if (kind == 0) {
                 A.npairs = ((uint64_t)F.rows_y * (uint64_t)NzG + 1u) / 2u;
                 for (int r = 0; r < F.rows_y; ++r) {
                     const long long ea = (long long)r * NzG + F.xk0, eb = ea + F.We - 1;
                     const long long qa = ea >> 1, qb = eb >> 1;
-                    q0.push_back(qa); npv.push_back((int)(qb - qa + 1));
+                    offv.push_back((int)(2 * qa - ea)); npv.push_back((int)(qb - qa + 1));
                     jumps.push_back(pcg_jump(4u * (uint64_t)qa, 1u));
                 }
             } else {
@@ -575,14 +656,14 @@ void build_device(dfb_filter_s& H) {
                 const bool touches = (P.k0 - M < 0) || (P.k1 + M > NzG);
                 if (M > 0 && touches)
                     for (int j = 0; j < Ny; ++j) {
-                        q0.push_back((long long)j * M); npv.push_back(M);
+                        offv.push_back(0); npv.push_back(M);
                         jumps.push_back(pcg_jump(4u * (uint64_t)j * (uint64_t)M, 1u));
                     }
             }
-            A.n_seg = (int)q0.size();
+            A.n_seg = (int)offv.size();
             for (int v : npv) max_np = std::max(max_np, v);
             if (A.n_seg) {
-                A.d_jump = H.upload(jumps); A.d_q0 = H.upload(q0); A.d_np = H.upload(npv);
+                A.d_jump = H.upload(jumps); A.d_off = H.upload(offv); A.d_np = H.upload(npv);
             }
             H.noise.push_back(A);
         }
@@ -591,6 +672,7 @@ void build_device(dfb_filter_s& H) {
     for (int t = 0; t < max_np; ++t) slot[t] = pcg_jump(4u * (uint64_t)t, 1u);
     H.np.slot_jump = H.upload(slot);
     H.np.max_np = max_np;
+    H.np.stride = pcg_jump(4u * (uint64_t)noise_stride_pairs(), 1u);
     H.np.chunks = (max_np + noise_threads() - 1) / noise_threads();
     CUDA_TRY(cudaStreamSynchronize(H.stream));
 }
@@ -600,7 +682,7 @@ void fill_noise_params(dfb_filter_s& H, int64_t step) {
     for (const NoiseHost& A : H.noise) {
         if (!A.n_seg) continue;
         NoiseArray& a = H.np.a[n];
-        a.seg_jump = A.d_jump; a.seg_q0 = static_cast<const long long*>(A.d_q0); a.seg_np = static_cast<const int*>(A.d_np);
+        a.seg_jump = A.d_jump; a.seg_off = static_cast<const int*>(A.d_off); a.seg_np = static_cast<const int*>(A.d_np);
         a.n_seg = A.n_seg; a.kind = A.kind; a.field = A.field;
         for (int p = 0; p < H.nplanes; ++p) {
             // stream ((plane*3 + field)*2 + array) of include/dfb_rng_spec.h; plane p of a batch is plane_id + p
@@ -648,7 +730,8 @@ void run_step(dfb_filter_s& H, double dt, bool first) {
     if (H.timing) CUDA_TRY(cudaEventRecord(H.ev[1], H.stream));
     if (H.noise_mode == DFB_NOISE_GENERATE && H.ybuf_step[b] == H.step) {
         // this step's y-sweep already ran (or is running) on the side stream; ev_noise[b] above covers it
-    } else if (H.tuned) CUDA_TRY(launch_ysweep_tma(H.maps[b], H.yp[b], H.n_tiles_dense, H.n_tiles_rec, H.stream));
+    } else if (H.tuned && H.y_form == 2) CUDA_TRY(launch_ysweep_run(H.rmaps[b], H.yp[b], H.stream));
+    else if (H.tuned) CUDA_TRY(launch_ysweep_tma(H.maps[b], H.yp[b], H.n_tiles_dense, H.n_tiles_rec, H.stream));
     else CUDA_TRY(launch_ysweep_simple(H.D[b], H.stream));
     if (H.timing) CUDA_TRY(cudaEventRecord(H.ev[2], H.stream));
     StepConsts S{};
@@ -682,7 +765,8 @@ void run_step(dfb_filter_s& H, double dt, bool first) {
         // ... and so does its y-sweep (it reads only that noise and writes only that set's r_zs interior): it
         // becomes resident as this step's z-sweep CTAs retire and keeps the fp64 pipe busy through the tail.
         if (H.tuned && H.y_ahead) {
-            CUDA_TRY(launch_ysweep_tma(H.maps[nb], H.yp[nb], H.n_tiles_dense, H.n_tiles_rec, H.side));
+            if (H.y_form == 2) CUDA_TRY(launch_ysweep_run(H.rmaps[nb], H.yp[nb], H.side));
+            else CUDA_TRY(launch_ysweep_tma(H.maps[nb], H.yp[nb], H.n_tiles_dense, H.n_tiles_rec, H.side));
             CUDA_TRY(cudaEventRecord(H.ev_noise[nb], H.side));      // "set nb is ready" now means noise + y-sweep
             H.ybuf_step[nb] = H.step;
         }
@@ -828,6 +912,8 @@ int dfb_info(dfb_handle h, int what, int field, int64_t* out64) {
         case 7: *out64 = h->tuned ? h->zp[0].zmode : 0; break;
         case 8: *out64 = h->tuned ? h->n_tiles_rec : 0; break;
         case 9: *out64 = h->tuned ? h->n_tiles_dense : 0; break;
+        case 10: *out64 = h->tuned ? h->y_form : -1; break;
+        case 11: *out64 = h->tuned ? h->yp[0].n_rtiles : 0; break;
         default: return fail(DFB_ERR_ARG, "unknown info selector");
     }
     return DFB_OK;

@@ -73,6 +73,29 @@ struct YTile {                 // up to Y_G consecutive groups x Y_TK columns
 
 struct YMaps { CUtensorMap m[3]; };
 
+// ---- y-sweep, run-recursive form (ysweep_run_kernel): row groups of <= YJ consecutive rows with ONE half-width ----
+constexpr int YR_C = 32;       // columns per tile = lanes of a warp (one column each)
+constexpr int YR_BOX = 32;     // padded rows per TMA box of the resident window
+#ifndef YR_CONSUMERS_N
+#define YR_CONSUMERS_N 8
+#endif
+constexpr int YR_CONSUMERS = YR_CONSUMERS_N;   // consumer warps of the persistent CTA (+ one producer warp).  Measured ms/step on 1024x2048 profile:
+                                               // 4: 0.141, 6: 0.123, 8: 0.115, 12: 0.121, 16: 0.123 -- the kernel is bound by shared-memory bandwidth, and the registers
+                                               // fewer warps leave free go to the next step's noise CTAs, which run beside it
+constexpr int YR_MAXG = 128;   // most groups a tile can hold (a block of 128 rows, every row its own group)
+struct YRGroup {               // 48 bytes
+    int j0, nrows, N, pad;
+    double a;                  // exp(-2 pi / N): ratio of neighbouring coefficients, b_i = a^|i| / s (df.cpp:168-177); 0 for N = 0
+    double a4;                 // a^4 (the Horner starts run as four interleaved chains)
+    double naN1;               // -a^(N+1): weight of the sample a sliding window drops
+    double inv_s;              // centre coefficient b_0 = 1 / s
+};
+struct YRTile {                // row block x 32 columns of one field; its whole input window is staged in shared memory
+    int field, col0, g0, ngroups;
+    int wlo, wrows;            // first padded row and row count of the window (union of the groups' windows)
+};
+struct YRMaps { CUtensorMap m[3]; };   // r_ys[f] with box {YR_C columns, YR_BOX rows}
+
 struct StepConsts {
     double sa[3], sb[3];       // sqrt(alpha), sqrt(1-alpha) per field (df.cpp:412-415), from the host's exp/sqrt
     int first_step;            // constructor semantics (df.cpp:57-62): no blend, T'/rho' untouched
@@ -81,20 +104,21 @@ struct StepConsts {
 // ---- noise generation work description (one segment = one row of one logical array) ----
 struct NoiseArray {
     const void* seg_jump;      // Jump[n_seg]: jump from `state` to the segment's first pair
-    const long long* seg_q0;   // first pair index of each segment (global pair index within the array)
+    const int* seg_off;        // r_ys: extended column of a segment's first pair, 2*q0 - (row * NzG + xk0); halo: 0
     const int* seg_np;         // pairs in each segment
     int n_seg;
     int kind;                  // 0 = r_ys rows, 1 = r_zs halo rows
     int field;
 };
 
-struct Jump;   // noise.cuh
+struct Jump { uint64_t A, C; };   // affine map of the LCG state over a number of draws: state' = A*state + inc*C (noise.cuh)
 
 struct NoiseParams {
     NoiseArray a[6];            // geometry of the (up to) six logical arrays, shared by the planes of a batch
     uint64_t pstate[DFB_MAXP][6];   // per plane and array: pcg32 state at the first draw of this step's array
     uint64_t pinc[DFB_MAXP][6];     //                      stream increment
     const Jump* slot_jump;      // (A, G) for delta = 4*t: state' = A*state + inc*G
+    Jump stride;                // (A, G) for the 4*NOISE_THREADS draws between two consecutive pairs of one thread
     int n_arrays;
     int max_np;                 // largest segment (pairs)
     int chunks;                 // ceil(max_np / 128)
@@ -108,6 +132,12 @@ struct YParams {
     int* zcounter;             // work counter of the z-sweep that follows (reset here)
     const double* yrec;        // recursive groups, 16 doubles per half-width N: a at [0], a^2, a^4, a^8 at [10..12]
     const double* ygc;         // recursive groups, 16 doubles each: factors of the low-bulk sum [0..7] and of the high-bulk sum [8..15] per output row
+    const YRGroup* rgroups;    // run-recursive form: groups and tiles (most expensive tile first), see ysweep_run_kernel
+    const YRTile* rtiles;
+    int n_rtiles;              // > 0: the run-recursive kernel is the y-sweep of this handle
+    int r_smem;                // its dynamic shared memory: control block + two window buffers
+    int r_wrows;               // rows of one window buffer (largest window, whole boxes)
+    int r_grid;                // CTAs of the persistent grid (one per SM)
     int tile0;                 // first tile of this launch in `tiles` (dense tiles first, then recursive tiles)
     int n_tiles;               // tiles of this launch (dense kernel: walked with stride gridDim.x)
     int tk;                    // columns per dense tile: 128, or 64 for planes that do not fill the GPU (never with recursive tiles)

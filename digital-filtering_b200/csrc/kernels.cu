@@ -21,13 +21,16 @@
 #ifndef Z_REC_MAXNREG
 #define Z_REC_MAXNREG 168
 #endif
-// pairs per thread of the noise kernel, processed one after the other (measured ms/step on 1024x2048 profile: 1 -> 0.158,
-// 2 -> 0.147, 4 -> 0.143, 8 -> 0.147, 16 -> 0.152): fewer, longer-lived CTAs slot in beside the sweeps' CTAs much better
+// pairs per thread of the noise kernel, NOISE_THREADS pairs apart (one position jump per thread, stride jumps between its pairs), two
+// in flight at a time (NOISE_UNROLL: the pair transform is one long dependent chain; with the run-recursive y-sweep and the z-sweep
+// resident beside it the noise kernel gets few warps per scheduler and needs the instruction-level parallelism).
+// Measured ms/step on 1024x2048 profile / 4096x8192 profile: pairs 4 unroll 1: 0.1170 / 1.537; 4, 2: 0.1151 / 1.526; 4, 4: 0.1144 / 1.499;
+// 8, 2: 0.1146 / 1.472
 #ifndef NOISE_PAIRS
-#define NOISE_PAIRS 4
+#define NOISE_PAIRS 8
 #endif
 #ifndef NOISE_UNROLL
-#define NOISE_UNROLL 1
+#define NOISE_UNROLL 2
 #endif
 #ifndef NOISE_THREADS
 #define NOISE_THREADS 128
@@ -46,63 +49,69 @@ __device__ __forceinline__ void tl_stamp(unsigned long long* tl, int end) {
 // =================================================================================================
 // H1: white noise
 // =================================================================================================
-__device__ __forceinline__ void noise_block1(const NoiseParams& P, const PlaneDev& D, int slot, int seg, int bz, int pl) {
+// One thread = NOISE_PAIRS pairs of one segment (row), NOISE_THREADS pairs apart, so that a warp's stores stay contiguous:
+// ONE position jump per thread (segment jump o slot jump, two table reads), then from pair to pair a constant stride jump
+// of 4*NOISE_THREADS draws -- one 64-bit multiply-add, like a plain LCG step -- instead of two table jumps per pair.
+__device__ __forceinline__ void noise_thread(const NoiseParams& P, const PlaneDev& D, int slot0, int seg, int bz, int pl) {
     const NoiseArray& A = P.a[bz];
-    const uint64_t A_state = P.pstate[pl][bz], A_inc = P.pinc[pl][bz];
     if (seg >= A.n_seg) return;
-    // all four table reads are requested together (the slot is clamped so that the read is always legal): one memory round trip
-    // per thread instead of two dependent ones
+    const uint64_t inc = P.pinc[pl][bz];
+    // the table reads are requested together: one memory round trip per thread
     const int np = A.seg_np[seg];
     const Jump sj = reinterpret_cast<const Jump*>(A.seg_jump)[seg];
-    const Jump tj = P.slot_jump[min(slot, P.max_np - 1)];
-    const long long q0 = A.seg_q0[seg];
-    if (slot >= np) return;
-    uint64_t s = sj.A * A_state + A_inc * sj.C;
-    s = tj.A * s + A_inc * tj.C;
-    double z0, z1;
-    normal_pair(s, A_inc, z0, z1);
-
-    const long long q = q0 + slot;
+    const Jump tj = P.slot_jump[min(slot0, P.max_np - 1)];
+    const int off = A.seg_off[seg];
+    if (slot0 >= np) return;
+    uint64_t s = sj.A * P.pstate[pl][bz] + inc * sj.C;
+    s = tj.A * s + inc * tj.C;
+    const uint64_t strideA = P.stride.A, strideC = inc * P.stride.C;
     const FieldDev& F = D.f[A.field];
     if (A.kind == 0) {
-        // r_ys: element e = r*NzG + g, segment = padded row r, g in [xk0, xk0+We)
-        const long long rowbase = (long long)seg * D.NzG + F.xk0;
-        const long long x0 = 2 * q - rowbase;
+        // r_ys: pair `slot` of padded row `seg` holds the extended columns x0 = 2 slot + off and x0 + 1 (off = 2 q0 - row base)
         double* dst = F.r_ys + (size_t)pl * F.ps_ys + (size_t)seg * F.pitch_y;
-        const bool in0 = x0 >= 0 && x0 < F.We, in1 = x0 + 1 >= 0 && x0 + 1 < F.We;
-        if (in0 && in1 && ((reinterpret_cast<uintptr_t>(dst + x0) & 15u) == 0)) {
-            *reinterpret_cast<double2*>(dst + x0) = make_double2(z0, z1);
-        } else {
-            if (in0) dst[x0] = z0;
-            if (in1) dst[x0 + 1] = z1;
+        int x0 = 2 * slot0 + off;
+        const bool vec_ok = (x0 & 1) == 0;                       // rows are 128-byte aligned: an even column is 16-byte aligned
+        constexpr int NU = NOISE_UNROLL;
+#pragma unroll NU
+        for (int slot = slot0; slot < np; slot += NOISE_THREADS, x0 += 2 * NOISE_THREADS) {
+            double z0, z1;
+            normal_pair(s, inc, z0, z1);
+            s = strideA * s + strideC;
+            const bool in0 = x0 >= 0 && x0 < F.We, in1 = x0 + 1 >= 0 && x0 + 1 < F.We;
+            if (in0 && in1 && vec_ok) {
+                *reinterpret_cast<double2*>(dst + x0) = make_double2(z0, z1);
+            } else {
+                if (in0) dst[x0] = z0;
+                if (in1) dst[x0 + 1] = z1;
+            }
+            if (slot + NOISE_THREADS >= slot0 + NOISE_PAIRS * NOISE_THREADS) break;
         }
     } else {
         // r_zs halo: element e = j*2M + h; h < M: global column h-M (left of the plane), else NzG + h-M
         const int M = F.Nz_max;
-        const long long e0 = 2 * q - (long long)seg * 2 * M;
         double* dst = F.r_zs + (size_t)pl * F.ps_zs + (size_t)seg * F.pitch_z + F.zoff;
         const int Wz = D.W + 2 * M;
+#pragma unroll 1
+        for (int slot = slot0, r = 0; slot < np && r < NOISE_PAIRS; slot += NOISE_THREADS, ++r) {
+            double z0, z1;
+            normal_pair(s, inc, z0, z1);
+            s = strideA * s + strideC;
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const int h = (int)e0 + i;
-            if (h < 0 || h >= 2 * M) continue;
-            const int g = h < M ? h - M : D.NzG + h - M;
-            const int c = g - (D.k0 - M);
-            if (c >= 0 && c < Wz) dst[c] = i ? z1 : z0;
+            for (int i = 0; i < 2; ++i) {
+                const int h = 2 * slot + i;
+                if (h >= 2 * M) continue;
+                const int g = h < M ? h - M : D.NzG + h - M;
+                const int c = g - (D.k0 - M);
+                if (c >= 0 && c < Wz) dst[c] = i ? z1 : z0;
+            }
         }
     }
-}
-
-__device__ __forceinline__ void noise_block(const NoiseParams& P, const PlaneDev& D, int bx, int seg, int bz, int pl) {
-    constexpr int NU = NOISE_UNROLL;
-#pragma unroll NU
-    for (int r = 0; r < NOISE_PAIRS; ++r) noise_block1(P, D, (bx * NOISE_PAIRS + r) * NOISE_THREADS + threadIdx.x, seg, bz, pl);
 }
 
 // one CTA per (NOISE_THREADS x NOISE_PAIRS pairs, segment, array x plane of the batch)
 __global__ void __launch_bounds__(NOISE_THREADS) noise_kernel(const NoiseParams P, const PlaneDev D) {
     if (threadIdx.x == 0 && (blockIdx.y & 31) == 0) tl_stamp(P.tl, 0);     // sampled: one row in 32 (same-address atomics)
-    noise_block(P, D, blockIdx.x, blockIdx.y, (int)(blockIdx.z % P.n_arrays), (int)(blockIdx.z / P.n_arrays));
+    noise_thread(P, D, (int)blockIdx.x * NOISE_PAIRS * NOISE_THREADS + (int)threadIdx.x, blockIdx.y, (int)(blockIdx.z % P.n_arrays), (int)(blockIdx.z / P.n_arrays));
     if (threadIdx.x == 0 && (blockIdx.y & 31) == 0) tl_stamp(P.tl, 1);
 }
 
@@ -549,6 +558,165 @@ __global__ void __launch_bounds__(160, 3) ysweep_rec_kernel(const __grid_constan
                 if (x + 1 < F.We) dst[x + 1] = v1;
             }
         }
+    }
+    if (lane == 0) tl_stamp(P.tl, 1);
+}
+
+// =================================================================================================
+// H2y tuned, run-recursive form: EVERY row group is evaluated through the exponential structure of the coefficients.
+//
+// b_i = a^|i| / s with a = exp(-2 pi / N) (df.cpp:168-177), so for a row j of half-width N
+//     out_j = (F_j + B_j - x_j) / s,   F_j = sum_{i=0..N} a^i x_{j-i},   B_j = sum_{i=0..N} a^i x_{j+i},
+// and inside a run of rows that share N both sums slide:  F_{j+1} = a F_j + x_{j+1} - a^(N+1) x_{j-N},
+// B_{j-1} = a B_j + x_{j-1} - a^(N+1) x_{j+N}.  The half-width changes every few rows on boundary-layer grids, so the
+// rows are cut into groups of <= 8 consecutive rows of ONE half-width (a lone row is a group of one); per group and
+// column: two Horner starts over N+1 samples each (run as four interleaved chains in a^4 per side: eight independent
+// FMA chains per thread) + 4 FMAs per further row -- 2(N+1) + 4R - 2 FMAs where the direct sum spends R(2N+1); 5x fewer
+// on the 1024x2048 boundary-layer profile, and no zero-padded band matrices at all.
+//
+// One tile = a block of up to 128 output rows x 32 columns of one field: its whole input window (block + 2 N_max rows)
+// is staged ONCE in shared memory by TMA (32-row boxes of cp.async.bulk.tensor.2d), 256 bytes per row: a warp reads one
+// row per LDS.64, conflict-free.  Persistent grid, one CTA per SM: a producer warp stages the next tile (window + the
+// tile's group descriptors, one mbarrier) into the second buffer while 16 consumer warps pull the current tile's groups
+// from a shared-memory counter (most expensive first); the consumers issue no global load at all.  Lanes are columns,
+// so a column's arithmetic does not depend on the tile or slab it sits in.  With every CTA resident from the start the
+// block scheduler has nothing of this kernel pending and lets the next step's noise CTAs in beside it.
+// Bound by shared-memory bandwidth (one 8-byte sample per FMA), not by the fp64 pipe.
+// Agreement with the reference's sequential sum: ~1e-15 of the rms (gate 1e-12).
+// =================================================================================================
+struct YRSmemCtl {                       // control block in front of the two window buffers
+    uint64_t full[2], empty[2];
+    int next_group[2];
+    YRTile tile[2];
+    int plane[2];
+    int pad[2];
+    alignas(16) YRGroup groups[2][YR_MAXG];      // cp.async.bulk destination
+};
+
+__global__ void __launch_bounds__(32 * (YR_CONSUMERS + 1), 1) ysweep_run_kernel(const __grid_constant__ YRMaps maps, const YParams P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    YRSmemCtl& ctl = *reinterpret_cast<YRSmemCtl*>(smem_raw);
+    constexpr size_t CTL = (sizeof(YRSmemCtl) + 127) / 128 * 128;
+    const size_t wbytes = (size_t)P.r_wrows * YR_C * sizeof(double);   // one window buffer (whole boxes)
+    const int nP = P.D.P;
+    const int n_all = P.n_rtiles * nP;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 2; ++s) { mbar_init(&ctl.full[s], 1); mbar_init(&ctl.empty[s], YR_CONSUMERS); }
+        mbar_fence_init();
+        if (blockIdx.x == 0 && P.zcounter) *P.zcounter = 0;      // the z-sweep that follows pulls its items from here
+        tl_stamp(P.tl, 0);
+    }
+    __syncthreads();
+    // Programmatic dependent launch: everything above overlapped the previous kernel's tail; the noise is read from here on
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
+    // Persistent: one CTA per SM walks the (most expensive first) tile list with stride gridDim.x through two window buffers.
+    if (warp == YR_CONSUMERS) {
+        // ---- producer: stages tile i+1 (window boxes + the tile's group descriptors) while the consumers work on tile i ----
+        if (lane == 0) {
+            int i = 0;
+            for (int tix = blockIdx.x; tix < n_all; tix += gridDim.x, ++i) {
+                const int s = i & 1;
+                if (i >= 2) mbar_wait(&ctl.empty[s], ((i >> 1) - 1) & 1);
+                const YRTile t = P.rtiles[tix / nP];
+                const int pl = tix % nP;
+                ctl.tile[s] = t; ctl.plane[s] = pl; ctl.next_group[s] = YR_CONSUMERS;
+                const int nbox = (t.wrows + YR_BOX - 1) / YR_BOX;
+                const uint32_t gbytes = (uint32_t)(t.ngroups * sizeof(YRGroup));
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the buffer was read through the generic proxy
+                mbar_expect_tx(&ctl.full[s], (uint32_t)(nbox * YR_BOX * YR_C * sizeof(double)) + gbytes);
+                double* win = reinterpret_cast<double*>(smem_raw + CTL + s * wbytes);
+                const int prow = pl * P.D.f[t.field].rows_y + t.wlo;
+                for (int b = 0; b < nbox; ++b)
+                    tma_load_2d(win + (size_t)b * YR_BOX * YR_C, &maps.m[t.field], t.col0, prow + b * YR_BOX, &ctl.full[s]);
+                tma_load_1d(&ctl.groups[s][0], P.rgroups + t.g0, gbytes, &ctl.full[s]);
+            }
+        }
+        return;
+    }
+
+    int i = 0;
+    for (int tix = blockIdx.x; tix < n_all; tix += gridDim.x, ++i) {
+        const int s = i & 1;
+        mbar_wait(&ctl.full[s], (i >> 1) & 1);
+        const YRTile& t = ctl.tile[s];
+        const int pl = ctl.plane[s];
+        const FieldDev& F = P.D.f[t.field];
+        const double* col = reinterpret_cast<const double*>(smem_raw + CTL + s * wbytes) + lane;   // sample of window row r: col[r * YR_C]
+        const int x = t.col0 + lane;                             // extended column
+        const bool live = x < F.We;
+        const int ngroups = t.ngroups, wlo = t.wlo;
+        for (int g = warp; g < ngroups;) {
+            const YRGroup& G = ctl.groups[s][g];
+            const int R = G.nrows, N = G.N;
+            const double a = G.a, a4 = G.a4, naN1 = G.naN1, inv_s = G.inv_s;
+            const int c = G.j0 + F.Ny_max - wlo;                 // window row of the group's first output row
+            const int ct = c + R - 1;                            // ... of its last
+            // ---- Horner starts: F at the first row over rows c-N..c, B at the last row over rows ct..ct+N; term i = 4 m + q goes to chain q ----
+            double f0 = 0.0, f1 = 0.0, f2 = 0.0, f3 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
+            {
+                int m = N >> 2;
+                const int i0 = 4 * m;                            // farthest terms: chains whose index exceeds N have nothing there
+                f0 = col[(c - i0) * YR_C]; b0 = col[(ct + i0) * YR_C];
+                if (i0 + 1 <= N) { f1 = col[(c - i0 - 1) * YR_C]; b1 = col[(ct + i0 + 1) * YR_C]; }
+                if (i0 + 2 <= N) { f2 = col[(c - i0 - 2) * YR_C]; b2 = col[(ct + i0 + 2) * YR_C]; }
+                if (i0 + 3 <= N) { f3 = col[(c - i0 - 3) * YR_C]; b3 = col[(ct + i0 + 3) * YR_C]; }
+                const double* pf = col + (size_t)(c - i0 + 4) * YR_C;   // term 4(m-1) of chain 0 on the F side
+                const double* pb = col + (size_t)(ct + i0 - 4) * YR_C;
+                // software pipeline: the eight samples of the next step are requested before the eight FMAs of this one
+                double nf0 = 0.0, nf1 = 0.0, nf2 = 0.0, nf3 = 0.0, nb0 = 0.0, nb1 = 0.0, nb2 = 0.0, nb3 = 0.0;
+                if (m > 0) {
+                    nf0 = pf[0]; nf1 = pf[-YR_C]; nf2 = pf[-2 * YR_C]; nf3 = pf[-3 * YR_C];
+                    nb0 = pb[0]; nb1 = pb[YR_C]; nb2 = pb[2 * YR_C]; nb3 = pb[3 * YR_C];
+                }
+#pragma unroll 2
+                for (--m; m >= 0; --m) {
+                    const double xf0 = nf0, xf1 = nf1, xf2 = nf2, xf3 = nf3, xb0 = nb0, xb1 = nb1, xb2 = nb2, xb3 = nb3;
+                    pf += 4 * YR_C; pb -= 4 * YR_C;
+                    if (m > 0) {
+                        nf0 = pf[0]; nf1 = pf[-YR_C]; nf2 = pf[-2 * YR_C]; nf3 = pf[-3 * YR_C];
+                        nb0 = pb[0]; nb1 = pb[YR_C]; nb2 = pb[2 * YR_C]; nb3 = pb[3 * YR_C];
+                    }
+                    f0 = __fma_rn(a4, f0, xf0); b0 = __fma_rn(a4, b0, xb0);
+                    f1 = __fma_rn(a4, f1, xf1); b1 = __fma_rn(a4, b1, xb1);
+                    f2 = __fma_rn(a4, f2, xf2); b2 = __fma_rn(a4, b2, xb2);
+                    f3 = __fma_rn(a4, f3, xf3); b3 = __fma_rn(a4, b3, xb3);
+                }
+            }
+            double Fc = __fma_rn(a, __fma_rn(a, __fma_rn(a, f3, f2), f1), f0);
+            double Bc = __fma_rn(a, __fma_rn(a, __fma_rn(a, b3, b2), b1), b0);
+            // ---- walks over the group's rows ----
+            double xr[YJ], Fv[YJ], xlo[YJ], xhi[YJ];
+#pragma unroll
+            for (int tt = 0; tt < YJ; ++tt) {
+                xr[tt] = tt < R ? col[(c + tt) * YR_C] : 0.0;
+                xlo[tt] = (tt >= 1 && tt < R) ? col[(c + tt - N - 1) * YR_C] : 0.0;      // what the window drops on the way up
+                xhi[tt] = tt < R - 1 ? col[(c + tt + N + 1) * YR_C] : 0.0;               // ... on the way down
+            }
+            Fv[0] = Fc;
+#pragma unroll
+            for (int tt = 1; tt < YJ; ++tt) {
+                if (tt < R) Fc = __fma_rn(naN1, xlo[tt], __fma_rn(a, Fc, xr[tt]));
+                Fv[tt] = Fc;
+            }
+            double* dst = F.r_zs + (size_t)pl * F.ps_zs + (size_t)G.j0 * F.pitch_z + F.zoff + F.yshift + x;   // r_zs interior (df.cpp:377)
+#pragma unroll
+            for (int tt = YJ - 1; tt >= 0; --tt) {
+                if (tt < R) {
+                    if (tt < R - 1) Bc = __fma_rn(naN1, xhi[tt], __fma_rn(a, Bc, xr[tt]));
+                    const double v = __dmul_rn(inv_s, __dsub_rn(__dadd_rn(Fv[tt], Bc), xr[tt]));
+                    if (live) dst[(size_t)tt * F.pitch_z] = v;
+                }
+            }
+            // next group of this tile
+            int nx = 0;
+            if (lane == 0) nx = atomicAdd(&ctl.next_group[s], 1);
+            g = __shfl_sync(0xffffffffu, nx, 0);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ctl.empty[s]);
     }
     if (lane == 0) tl_stamp(P.tl, 1);
 }
@@ -1078,6 +1246,7 @@ constexpr int Y_RC = 8, Y_NS = 6;
 
 size_t ysweep_smem_bytes() { return sizeof(YSmem<Y_RC, Y_NS>); }
 int noise_threads() { return NOISE_THREADS * NOISE_PAIRS; }
+int noise_stride_pairs() { return NOISE_THREADS; }
 int ysweep_rc() { return Y_RC; }
 
 cudaError_t ysweep_prepare() {
@@ -1141,6 +1310,21 @@ cudaError_t launch_ysweep_tma(const YMaps& maps, const YParams& P, int n_dense, 
     return cudaSuccess;
 }
 
+size_t ysweep_run_smem(int wrows) { return (sizeof(YRSmemCtl) + 127) / 128 * 128 + (size_t)2 * wrows * YR_C * sizeof(double); }
+
+cudaError_t ysweep_run_prepare(size_t smem) {
+    cudaError_t e = cudaFuncSetAttribute(ysweep_run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(ysweep_run_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+
+cudaError_t launch_ysweep_run(const YRMaps& maps, const YParams& P, cudaStream_t st) {
+    cudaLaunchAttribute attr;
+    const int n_all = P.n_rtiles * P.D.P;
+    cudaLaunchConfig_t cfg = pdl_config((unsigned)(n_all < P.r_grid ? n_all : P.r_grid), 32 * (YR_CONSUMERS + 1), (size_t)P.r_smem, st, &attr);
+    return cudaLaunchKernelEx(&cfg, ysweep_run_kernel, maps, P);
+}
+
 static const void* zsweep_fn(int zk, int mode, bool stats) {
     if (stats) {
         if (zk == 16) return mode == 1 ? (const void*)zsweep_epilogue_kernel<16, 1, true> : (const void*)zsweep_epilogue_kernel<16, 0, true>;
@@ -1164,6 +1348,8 @@ cudaError_t zsweep_prepare(int zk, int mode, size_t smem, int* blocks_per_sm) {
 cudaError_t launch_zsweep_tuned(const ZMaps& maps, const ZParams& P, cudaStream_t st) {
     cudaLaunchAttribute attr;
     cudaLaunchConfig_t cfg = pdl_config((unsigned)P.nblocks, 128, (size_t)P.smem_bytes, st, &attr);
+    static const int pdl = std::getenv("DFB_Z_PDL") ? std::atoi(std::getenv("DFB_Z_PDL")) : 1;
+    if (!pdl) cfg.numAttrs = 0;
     void* args[2] = {const_cast<ZMaps*>(&maps), const_cast<ZParams*>(&P)};
     return cudaLaunchKernelExC(&cfg, zsweep_fn(P.zk, P.zmode, P.stats != nullptr), args);
 }

@@ -6,10 +6,10 @@
 #pragma once
 #include <cstdint>
 #include "dfb_rng_spec.h"
+#include "device.cuh"
 
 namespace dfb {
 
-struct Jump { uint64_t A, C; };   // state' = A*state + C
 
 __host__ __device__ inline uint64_t pcg_lcg(uint64_t s, uint64_t inc) { return s * DFB_PCG32_MULT + inc; }
 

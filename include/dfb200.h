@@ -110,7 +110,9 @@ int dfb_dims(dfb_handle h, int* Ny, int* Nz);
 /* what = 0 Ny_max, 1 Nz_max (per field f), 2 step counter, 3 row-uniform fast path in use (0/1),
  * 4 algorithmic tap-FMAs per step (as int64 via out64), 5 global Nz, 6 CUDA device ordinal,
  * 7 form of the z-sweep in use: 1 = recursive evaluation of the exponential window, 0 = direct Toeplitz sum,
- * 8 / 9 y-sweep tiles evaluated recursively / with dense band matrices */
+ * 8 / 9 y-sweep tiles of the band-matrix kernels evaluated recursively / with dense band matrices,
+ * 10 form of the y-sweep in use: 2 = run-recursive (every row group through the exponential window, the default), 1 = chunk-recursive
+ *    band-matrix kernel, 0 = dense band matrices (DFB_Y_MODE forces a form), 11 tiles of the run-recursive kernel */
 int dfb_info(dfb_handle h, int what, int field, int64_t* out64);
 /* host copies of the setup tables (for parity tests): which = 0..7 rows R11,R21,R22,R33,Us,Ts,rhos,Ms [Ny];
  * 8 yc row [Ny]; 9 dy row [Ny]; 10 Lt[3]; 11 coefficients of half-width `arg` [2*arg+1];

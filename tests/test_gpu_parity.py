@@ -458,13 +458,16 @@ def test_large_half_widths_beyond_128(dfb, O, W):
     assert _run_explicit(dfb, O, plane, seed=13, dts=[3e-7])
 
 
-@pytest.mark.parametrize("ymode", ["1", "0"], ids=["y-recursive", "y-dense"])
+@pytest.mark.parametrize("ymode", ["2", "1", "0"], ids=["y-run-recursive", "y-chunk-recursive", "y-dense"])
 def test_G2_both_forms_of_the_y_sweep(dfb, O, W, monkeypatch, ymode):
-    """The tuned y-sweep evaluates row groups with one half-width N >= 16 recursively (ysweep_rec_kernel) and everything else with
-    dense band matrices; by default the recursive kernel is only switched on for (nearly) uniform planes.  Forced on and forced
-    off, on a boundary-layer profile (N_y changes every few rows: runs of every length, mixed leftovers) and on hand-made runs
+    """The tuned y-sweep has three forms: run-recursive (ysweep_run_kernel, the default: every group of <= 8 rows of one half-width
+    through the exponential window), and the band-matrix kernels kept for windows too tall for shared memory -- chunk-recursive
+    (ysweep_rec_kernel) and dense.  Each forced in turn, on a boundary-layer profile (N_y changes every few rows: runs of every length, mixed leftovers) and on hand-made runs
     (lengths 1..20, N from 2 to 200, windows not aligned to the 8-row chunks), both must pass the gate."""
     monkeypatch.setenv("DFB_Y_MODE", ymode)
+    probe = dfb.DIGITAL_FILTER(dfb.DFConfig.from_plane(W.plane_profile(200, 300, 96, 24), noise_mode=dfb.NOISE_INJECT))
+    assert probe.info(10) == int(ymode)
+    probe.close()
     worst = inject_and_step(dfb, O, W.plane_profile(200, 300, 96, 24), 0, seed=23, dts=[2e-7, 8e-7])
     assert max(worst.values()) < 1e-13, worst
     rng = np.random.default_rng(7)
