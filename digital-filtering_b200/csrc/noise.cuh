@@ -1,4 +1,4 @@
-// csrc/noise.cuh -- device side of the white-noise contract in include/dfb_rng_spec.h (spec v1).
+// csrc/noise.cuh -- device side of the white-noise contract in include/dfb_rng_spec.h (spec v2).
 // Replaces DIGITAL_FILTER::generate_white_noise (df.cpp:332-349): per-element pcg32 streams
 // (pcg_random.hpp:1866) addressed by jump-ahead (pcg_random.hpp:640-669) instead of one serial
 // process-wide stream, and a Box-Muller pair transform made only of correctly rounded IEEE
@@ -37,7 +37,9 @@ inline Jump pcg_jump(uint64_t delta, uint64_t inc) {
 }
 
 #ifdef __CUDACC__
-__constant__ double c_log[DFB_LOG_NC] = {DFB_LOG_C_LIST};
+__constant__ double c_log1p[DFB_LOG1P_NC] = {DFB_LOG1P_C_LIST};
+// per-lane index: global memory through the read-only path (a __constant__ table would serialise the divergent lookups)
+__device__ const double2 g_logtab[64] = {DFB_LOGTAB_LIST};
 __constant__ double c_sin[DFB_SIN_NC] = {DFB_SIN_C_LIST};
 __constant__ double c_cos[DFB_COS_NC] = {DFB_COS_C_LIST};
 
@@ -48,22 +50,21 @@ __device__ __forceinline__ void normal_pair(uint64_t state, uint64_t inc, double
     uint32_t o1 = pcg_xsh_rr(state); state = pcg_lcg(state, inc);
     uint32_t o2 = pcg_xsh_rr(state); state = pcg_lcg(state, inc);
     uint32_t o3 = pcg_xsh_rr(state);
-    uint64_t U1 = ((((uint64_t)o1 << 32) | o0) >> 11) + 1u;
+    uint64_t U1 = ((((uint64_t)o1 << 32) | o0) >> 11) | 1u;
     uint64_t U2 = (((uint64_t)o3 << 32) | o2) >> 11;
 
-    double d = __ull2double_rn(U1);                         // exact: U1 <= 2^53
+    double d = __ull2double_rn(U1);                         // exact: U1 < 2^53
     uint64_t bits = (uint64_t)__double_as_longlong(d);
-    int E = (int)(bits >> 52) - 1023;
-    double m = __longlong_as_double((long long)((bits & 0x000FFFFFFFFFFFFFULL) | 0x3FF0000000000000ULL));
-    if (m > DFB_SQRT2) { m = __dmul_rn(m, 0.5); E += 1; }
-    double f = __dadd_rn(m, -1.0);
-    double s = __ddiv_rn(f, __dadd_rn(2.0, f));
-    double zz = __dmul_rn(s, s);
-    double P = c_log[DFB_LOG_NC - 1];
+    const unsigned i6 = (unsigned)(bits >> 46) & 63u, hi = i6 >> 5;
+    const int e = (int)(bits >> 52) - 1023 + (int)hi - 53;
+    const double m = __longlong_as_double((long long)((bits & 0x000FFFFFFFFFFFFFULL) | ((uint64_t)(0x3FFu - hi) << 52)));
+    const double2 tab = __ldg(&g_logtab[i6]);               // (INV, L)
+    const double rr = __fma_rn(m, tab.x, -1.0);
+    double P = c_log1p[DFB_LOG1P_NC - 1];
 #pragma unroll
-    for (int k = DFB_LOG_NC - 2; k >= 0; --k) P = __fma_rn(P, zz, c_log[k]);
-    double lnm = __fma_rn(__dmul_rn(s, zz), P, __dmul_rn(2.0, s));
-    double lnu = __fma_rn((double)(E - 53), DFB_LN2, lnm);
+    for (int k = DFB_LOG1P_NC - 2; k >= 0; --k) P = __fma_rn(P, rr, c_log1p[k]);
+    const double lp = __fma_rn(__dmul_rn(rr, rr), P, rr);
+    const double lnu = __fma_rn((double)e, DFB_LN2, __dadd_rn(tab.y, lp));
     double r = __dsqrt_rn(__dmul_rn(-2.0, lnu));
 
     unsigned oct = (unsigned)(U2 >> 50);

@@ -1,5 +1,5 @@
 /* oracle/normal_oracle.c -- TEST INFRASTRUCTURE ONLY.  Host restatement of the noise contract in
- * include/dfb_rng_spec.h (spec v1): counter-addressed pcg32 draws (the reference's engine,
+ * include/dfb_rng_spec.h (spec v2): counter-addressed pcg32 draws (the reference's engine,
  * pcg_random.hpp:1866, advanced with its own jump-ahead algorithm, pcg_random.hpp:640-669) fed
  * through a Box-Muller pair transform made only of correctly rounded IEEE operations.
  * Compiled with -ffp-contract=off; every fused operation is an explicit fma().
@@ -16,29 +16,28 @@ void orc_pcg32_seed(orc_pcg32* g, uint64_t seed, uint64_t stream);
 void orc_pcg32_advance(orc_pcg32* g, uint64_t delta);
 uint32_t orc_pcg32_next(orc_pcg32* g);
 
-static const double LOG_C[DFB_LOG_NC] = {DFB_LOG_C_LIST};
+static const double LOG1P_C[DFB_LOG1P_NC] = {DFB_LOG1P_C_LIST};
+static const double LOGTAB[128] = {DFB_LOGTAB_LIST};        /* INV[i] at 2i, L[i] at 2i+1 */
 static const double SIN_C[DFB_SIN_NC] = {DFB_SIN_C_LIST};
 static const double COS_C[DFB_COS_NC] = {DFB_COS_C_LIST};
 
 /* four consecutive 32-bit draws -> two N(0,1) doubles */
 void orc_normal_pair(const uint32_t o[4], double z[2]) {
-    uint64_t U1 = ((((uint64_t)o[1] << 32) | o[0]) >> 11) + 1u;
+    uint64_t U1 = ((((uint64_t)o[1] << 32) | o[0]) >> 11) | 1u;
     uint64_t U2 = (((uint64_t)o[3] << 32) | o[2]) >> 11;
 
-    /* ln(u1), u1 = U1 * 2^-53 */
+    /* ln(u1), u1 = U1 * 2^-53: table over the top six mantissa bits + log1p polynomial */
     double d = (double)U1;
     uint64_t bits; memcpy(&bits, &d, 8);
-    int E = (int)(bits >> 52) - 1023;
-    uint64_t mb = (bits & 0x000FFFFFFFFFFFFFULL) | 0x3FF0000000000000ULL;
+    unsigned i6 = (unsigned)(bits >> 46) & 63u, hi = i6 >> 5;
+    int e = (int)(bits >> 52) - 1023 + (int)hi - 53;
+    uint64_t mb = (bits & 0x000FFFFFFFFFFFFFULL) | ((uint64_t)(0x3FFu - hi) << 52);
     double m; memcpy(&m, &mb, 8);
-    if (m > DFB_SQRT2) { m = m * 0.5; E += 1; }
-    double f = m - 1.0;
-    double s = f / (2.0 + f);
-    double zz = s * s;
-    double P = LOG_C[DFB_LOG_NC - 1];
-    for (int k = DFB_LOG_NC - 2; k >= 0; --k) P = fma(P, zz, LOG_C[k]);
-    double lnm = fma(s * zz, P, 2.0 * s);
-    double lnu = fma((double)(E - 53), DFB_LN2, lnm);
+    double rr = fma(m, LOGTAB[2 * i6], -1.0);
+    double P = LOG1P_C[DFB_LOG1P_NC - 1];
+    for (int k = DFB_LOG1P_NC - 2; k >= 0; --k) P = fma(P, rr, LOG1P_C[k]);
+    double lp = fma(rr * rr, P, rr);
+    double lnu = fma((double)e, DFB_LN2, LOGTAB[2 * i6 + 1] + lp);
     double r = sqrt(-2.0 * lnu);
 
     /* sin/cos(2 pi u2), u2 = U2 * 2^-53 : octant from the top 3 bits, 50-bit fraction */

@@ -11,7 +11,7 @@ def test_pair_transform_matches_libm_to_a_few_ulp(O):
     for _ in range(2000):
         o = rng.integers(0, 2 ** 32, 4, dtype=np.uint64).astype(np.uint32)
         z = O.normal_pair(o)
-        U1 = (((int(o[1]) << 32) | int(o[0])) >> 11) + 1
+        U1 = (((int(o[1]) << 32) | int(o[0])) >> 11) | 1
         U2 = ((int(o[3]) << 32) | int(o[2])) >> 11
         r = math.sqrt(-2.0 * math.log(U1 / 2.0 ** 53))
         th = 2.0 * math.pi * (U2 / 2.0 ** 53)
