@@ -63,6 +63,18 @@ def lib():
         if not os.path.exists(LIB_PATH):
             raise ImportError(f"{LIB_PATH} is not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
                               "(make -C digital-filtering_b200/csrc). There is no CPU fallback.")
+        # libdfb200.so links libnccl.so.2 (config 4's hand-off).  If PyTorch's bundled NCCL is installed, bring that copy in first so that
+        # the process holds ONE NCCL whichever of torch / this library is imported first (same soname: the loader would otherwise hand
+        # torch the system copy, which may be older than the one it was built against).
+        try:
+            import importlib.util
+            spec = importlib.util.find_spec("nvidia.nccl")
+            if spec and spec.submodule_search_locations:
+                cand = os.path.join(list(spec.submodule_search_locations)[0], "lib", "libnccl.so.2")
+                if os.path.exists(cand):
+                    C.CDLL(cand, mode=C.RTLD_GLOBAL)
+        except Exception:
+            pass
         L = C.CDLL(LIB_PATH)
         L.dfb_last_error.restype = C.c_char_p
         L.dfb_version.restype = C.c_char_p
@@ -76,6 +88,15 @@ def lib():
         L.dfb_write_rms_csv.argtypes = [C.c_void_p, C.c_char_p]
         L.dfb_write_tecplot.argtypes = [C.c_void_p, C.c_char_p]
         L.dfb_face_map.argtypes = [C.c_void_p, C.c_int, c_dp, c_dp, c_ip]
+        L.dfb_comm_unique_id.argtypes = [C.c_void_p]
+        L.dfb_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.dfb_comm_info.argtypes = [C.c_void_p, c_ip, c_ip, c_ip]
+        L.dfb_gather_begin.argtypes = [C.c_void_p, C.c_int]
+        L.dfb_gather_end.argtypes = [C.c_void_p]
+        L.dfb_gathered_ptr.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+        L.dfb_gathered_to_host.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.dfb_gather_wire_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+        L.dfb_comm_destroy.argtypes = [C.c_void_p]
         for name in ("dfb_destroy", "dfb_sync", "dfb_first_step"):
             getattr(L, name).argtypes = [C.c_void_p]
         L.dfb_dims.argtypes = [C.c_void_p, c_ip, c_ip]
@@ -423,6 +444,47 @@ class DIGITAL_FILTER:
         out = np.zeros(len(yf), dtype=np.int32)
         _check(lib().dfb_face_map(self._h, len(yf), _dptr(yf), _dptr(zf), out.ctypes.data_as(c_ip)))
         return out
+
+    # ---- config 4: this handle as one spanwise slab of a plane shared with the other ranks (NCCL inside the library) ----
+    @staticmethod
+    def comm_unique_id():
+        """rank 0: the 128-byte NCCL id every rank passes to comm_init (ship it with the job's own means)"""
+        buf = C.create_string_buffer(128)
+        _check(lib().dfb_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, ident, rank, world):
+        _check(lib().dfb_comm_init(self._h, C.c_char_p(ident), int(rank), int(world)))
+        self._NzG = self.info(5)
+
+    def comm_bounds(self):
+        r, w = C.c_int(), C.c_int()
+        _check(lib().dfb_comm_info(self._h, C.byref(r), C.byref(w), None))
+        b = np.zeros(2 * w.value, dtype=np.int32)
+        _check(lib().dfb_comm_info(self._h, None, None, b.ctypes.data_as(c_ip)))
+        return [(int(b[2 * i]), int(b[2 * i + 1])) for i in range(w.value)]
+
+    def gather_begin(self, dst=0):
+        _check(lib().dfb_gather_begin(self._h, int(dst)))
+
+    def gather_end(self):
+        _check(lib().dfb_gather_end(self._h))
+
+    def gathered(self, which, out=None):
+        """destination rank: host copy (Ny, Nz_global) of a gathered field"""
+        out = np.zeros((self.Ny, self._NzG)) if out is None else out
+        _check(lib().dfb_gathered_to_host(self._h, which, out.ctypes.data))
+        return out
+
+    def gathered_ptr(self, which):
+        p = C.c_void_p()
+        _check(lib().dfb_gathered_ptr(self._h, which, C.byref(p)))
+        return p.value
+
+    def gather_wire_bytes(self):
+        v = C.c_int64()
+        _check(lib().dfb_gather_wire_bytes(self._h, C.byref(v)))
+        return v.value
 
     # ---- timing ----
     def set_timing(self, on=True):

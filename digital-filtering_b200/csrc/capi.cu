@@ -9,6 +9,7 @@
 #include <memory>
 #include <string>
 #include <vector>
+#include <nccl.h>
 #include "dfb200.h"
 #include "plan.hpp"
 #include "noise.cuh"
@@ -91,11 +92,25 @@ struct dfb_filter_s {
     double* stats = nullptr;          // [P][6][Ny*W]: sum u'^2, v'^2, w'^2, T'^2, rho'^2, u'v'
     int64_t stats_count = 0;
     bool stats_on = false;
+    // config 4: this handle as one spanwise slab of a plane shared with the other ranks of a job (dfb_comm_init)
+    ncclComm_t comm = nullptr;
+    int comm_rank = -1, comm_world = 0;
+    std::vector<int> comm_bounds;     // [2*world]: k_begin, k_end of every rank
+    cudaStream_t comm_stream = nullptr;
+    double* g_send = nullptr;         // staged u', v', w' of this slab: [3][Ny][W]
+    double* g_recv = nullptr;         // dst rank: every rank's staged slab back to back, [rank][3][Ny][W_rank]
+    double* g_plane = nullptr;        // dst rank: the assembled plane, [5][Ny][NzG]
+    std::vector<size_t> g_recv_off;   // offsets (doubles) of the ranks' slabs in g_recv
+    cudaEvent_t ev_gstaged = nullptr, ev_gdone = nullptr;
+    int g_dst = -1;
+    int64_t g_begun = 0, g_ended = 0, g_bytes_wire = 0;
+    bool g_after_first_only = false;  // the gathered step was the constructor's: T', rho' are zero (df.cpp:57-65)
     // timing
     bool timing = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     float last_ms[4] = {0, 0, 0, 0};
 
+    void comm_release();              // ncclCommDestroy through the lazily loaded library (below)
     template <class T>
     T* dalloc(size_t n, bool zero = true) {
         void* p = nullptr;
@@ -118,6 +133,11 @@ struct dfb_filter_s {
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         for (int b = 0; b < 2; ++b) { if (ev_noise[b]) cudaEventDestroy(ev_noise[b]); if (ev_free[b]) cudaEventDestroy(ev_free[b]); }
         for (int q = 0; q < 2; ++q) { if (ev_staged[q]) cudaEventDestroy(ev_staged[q]); if (ev_copied[q]) cudaEventDestroy(ev_copied[q]); }
+        if (comm_stream) cudaStreamSynchronize(comm_stream);
+        if (ev_gstaged) cudaEventDestroy(ev_gstaged);
+        if (ev_gdone) cudaEventDestroy(ev_gdone);
+        comm_release();
+        if (comm_stream) cudaStreamDestroy(comm_stream);
         if (copy) cudaStreamDestroy(copy);
         if (side) cudaStreamDestroy(side);
         if (stream) cudaStreamDestroy(stream);
@@ -1377,6 +1397,203 @@ int dfb_debug_zprof(dfb_handle h, unsigned long long* out8) {
         CUDA_TRY(cudaMemset(h->zp[0].prof, 0, 64));
     });
 }
+
+}  // extern "C" (the comm section below reopens it)
+
+// =================================================================================================
+// BASELINE config 4 -- one plane in spanwise slabs over the ranks of a job; NCCL only for the hand-off of the finished
+// plane to the CFD rank (README.md:55 "MPI support to distribute result"; us3d_user.f90:85-92).
+// =================================================================================================
+namespace {
+
+// NCCL is a link-time dependency of libdfb200.so (libnccl.so.2: the system copy, or the one a host framework such as PyTorch
+// has already loaded under the same soname)
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = ncclGetUniqueId;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = ncclCommInitRank;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = ncclCommDestroy;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = ncclSend;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = ncclRecv;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = ncclAllGather;
+    ncclResult_t (*GroupStart)() = ncclGroupStart;
+    ncclResult_t (*GroupEnd)() = ncclGroupEnd;
+    const char* (*GetErrorString)(ncclResult_t) = ncclGetErrorString;
+};
+
+NcclApi& nccl() {
+    static NcclApi api;
+    return api;
+}
+
+#define NCCL_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        ncclResult_t r__ = (expr);                                                                       \
+        if (r__ != ncclSuccess) throw Error{DFB_ERR_CUDA, std::string(#expr) + ": " + nccl().GetErrorString(r__)};   \
+    } while (0)
+
+}  // namespace
+
+void dfb_filter_s::comm_release() {
+    if (comm) { try { nccl().CommDestroy(comm); } catch (...) {} comm = nullptr; }
+}
+
+extern "C" {
+
+int dfb_comm_unique_id(void* id128) {
+    if (!id128) return fail(DFB_ERR_ARG, "id128 is NULL");
+    static_assert(sizeof(ncclUniqueId) == DFB_COMM_ID_BYTES, "ncclUniqueId is 128 bytes");
+    return guarded([&] { NCCL_TRY(nccl().GetUniqueId(static_cast<ncclUniqueId*>(id128))); });
+}
+
+int dfb_comm_init(dfb_handle h, const void* id128, int rank, int world) {
+    if (!h || !id128 || world < 1 || rank < 0 || rank >= world) return fail(DFB_ERR_ARG, "bad argument");
+    if (h->comm) return fail(DFB_ERR_STATE, "dfb_comm_init was already called on this handle");
+    if (h->nplanes != 1) return fail(DFB_ERR_STATE, "slab communication is defined for single-plane handles");
+    return guarded([&] {
+        CUDA_TRY(cudaSetDevice(h->device));
+        ncclUniqueId id;
+        std::memcpy(&id, id128, sizeof(id));
+        NCCL_TRY(nccl().CommInitRank(&h->comm, world, id, rank));
+        h->comm_rank = rank; h->comm_world = world;
+        CUDA_TRY(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&h->ev_gstaged, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&h->ev_gdone, cudaEventDisableTiming));
+        // every rank learns every rank's slab: one all-gather of (k_begin, k_end, Ny, Nz_global)
+        int mine[4] = {h->plan.k0, h->plan.k1, h->plan.Ny, h->plan.NzG};
+        int* d = h->dalloc<int>((size_t)4 * (world + 1));
+        CUDA_TRY(cudaMemcpyAsync(d, mine, sizeof(mine), cudaMemcpyHostToDevice, h->comm_stream));
+        NCCL_TRY(nccl().AllGather(d, d + 4, 4, ncclInt32, h->comm, h->comm_stream));
+        std::vector<int> all((size_t)4 * world);
+        CUDA_TRY(cudaMemcpyAsync(all.data(), d + 4, all.size() * sizeof(int), cudaMemcpyDeviceToHost, h->comm_stream));
+        CUDA_TRY(cudaStreamSynchronize(h->comm_stream));
+        h->comm_bounds.resize((size_t)2 * world);
+        for (int r = 0; r < world; ++r) {
+            if (all[4 * r + 2] != h->plan.Ny || all[4 * r + 3] != h->plan.NzG)
+                throw Error{DFB_ERR_ARG, "the ranks of a slab job must describe the same plane (Ny, Nz differ on rank " + std::to_string(r) + ")"};
+            h->comm_bounds[2 * r] = all[4 * r]; h->comm_bounds[2 * r + 1] = all[4 * r + 1];
+        }
+        for (int r = 0; r + 1 < world; ++r)
+            if (h->comm_bounds[2 * r + 1] != h->comm_bounds[2 * r + 2])
+                throw Error{DFB_ERR_ARG, "slabs must tile the plane in rank order (rank r's k_end = rank r+1's k_begin)"};
+        if (h->comm_bounds[0] != 0 || h->comm_bounds[2 * world - 1] != h->plan.NzG)
+            throw Error{DFB_ERR_ARG, "slabs must cover [0, Nz)"};
+        h->g_send = h->dalloc<double>((size_t)3 * h->D[0].ps_cells, false);
+    });
+}
+
+int dfb_comm_info(dfb_handle h, int* rank, int* world, int* bounds) {
+    if (!h) return fail(DFB_ERR_ARG, "handle is NULL");
+    if (!h->comm) return fail(DFB_ERR_STATE, "dfb_comm_init has not been called");
+    if (rank) *rank = h->comm_rank;
+    if (world) *world = h->comm_world;
+    if (bounds) std::memcpy(bounds, h->comm_bounds.data(), h->comm_bounds.size() * sizeof(int));
+    return DFB_OK;
+}
+
+int dfb_gather_begin(dfb_handle h, int dst_rank) {
+    if (!h) return fail(DFB_ERR_ARG, "handle is NULL");
+    if (!h->comm) return fail(DFB_ERR_STATE, "dfb_comm_init has not been called");
+    if (dst_rank < 0 || dst_rank >= h->comm_world) return fail(DFB_ERR_ARG, "dst_rank out of range");
+    if (h->g_begun != h->g_ended) return fail(DFB_ERR_STATE, "a gather is already outstanding: call dfb_gather_end first");
+    return guarded([&] {
+        CUDA_TRY(cudaSetDevice(h->device));
+        const int Ny = h->plan.Ny, NzG = h->plan.NzG, world = h->comm_world;
+        const size_t n = h->D[0].ps_cells;
+        const bool dst = h->comm_rank == dst_rank;
+        if (dst && (!h->g_plane || h->g_dst != dst_rank)) {
+            if (!h->g_plane) {
+                h->g_plane = h->dalloc<double>((size_t)5 * Ny * NzG);
+                h->g_recv = h->dalloc<double>((size_t)3 * Ny * NzG, false);
+                h->g_recv_off.assign(world + 1, 0);
+                for (int r = 0; r < world; ++r)
+                    h->g_recv_off[r + 1] = h->g_recv_off[r] + (size_t)3 * Ny * (h->comm_bounds[2 * r + 1] - h->comm_bounds[2 * r]);
+            }
+        }
+        h->g_dst = dst_rank;
+        h->g_after_first_only = h->step <= 1;
+        // stage u', v', w' of the step just enqueued (device to device, on the compute stream: the next step may overwrite the
+        // fields as soon as this copy is done); the wire carries these 24 bytes per cell -- T', rho' are row-wise multiples of u'
+        // (df.cpp:470-485) and are rebuilt on the destination
+        double* stage = dst ? h->g_recv + h->g_recv_off[h->comm_rank] : h->g_send;
+        CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_gdone, 0));        // the previous gather has shipped the staging buffer
+        for (int f = 0; f < 3; ++f)
+            CUDA_TRY(cudaMemcpyAsync(stage + (size_t)f * n, field_ptr(*h, f), n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        CUDA_TRY(cudaEventRecord(h->ev_gstaged, h->stream));
+        CUDA_TRY(cudaStreamWaitEvent(h->comm_stream, h->ev_gstaged, 0));
+        h->g_bytes_wire = 0;
+        if (world > 1) {
+            NCCL_TRY(nccl().GroupStart());
+            if (dst) {
+                for (int r = 0; r < world; ++r) {
+                    if (r == dst_rank) continue;
+                    const size_t cnt = h->g_recv_off[r + 1] - h->g_recv_off[r];
+                    NCCL_TRY(nccl().Recv(h->g_recv + h->g_recv_off[r], cnt, ncclDouble, r, h->comm, h->comm_stream));
+                    h->g_bytes_wire += (int64_t)cnt * 8;
+                }
+            } else {
+                NCCL_TRY(nccl().Send(h->g_send, 3 * n, ncclDouble, dst_rank, h->comm, h->comm_stream));
+                h->g_bytes_wire = (int64_t)3 * n * 8;
+            }
+            NCCL_TRY(nccl().GroupEnd());
+        }
+        if (dst) {
+            // [rank][3][Ny][W_rank] -> row-major planes u', v', w' + T', rho' rebuilt with the row constants (bitwise what the slabs hold)
+            std::vector<int> b(h->comm_bounds);
+            CUDA_TRY(launch_assemble(h->g_recv, h->g_plane, h->D[0].rowc, Ny, NzG, world, b.data(), h->g_after_first_only ? 1 : 0, h->comm_stream));
+        }
+        CUDA_TRY(cudaEventRecord(h->ev_gdone, h->comm_stream));
+        h->g_begun += 1;
+    });
+}
+
+int dfb_gather_end(dfb_handle h) {
+    if (!h) return fail(DFB_ERR_ARG, "handle is NULL");
+    if (!h->comm) return fail(DFB_ERR_STATE, "dfb_comm_init has not been called");
+    if (h->g_begun == h->g_ended) return fail(DFB_ERR_STATE, "no dfb_gather_begin is outstanding");
+    return guarded([&] {
+        CUDA_TRY(cudaSetDevice(h->device));
+        CUDA_TRY(cudaEventSynchronize(h->ev_gdone));
+        h->g_ended += 1;
+    });
+}
+
+int dfb_gathered_ptr(dfb_handle h, int which, void** ptr) {
+    if (!h || !ptr || which < 0 || which > 4) return fail(DFB_ERR_ARG, "bad argument");
+    if (!h->g_plane) return fail(DFB_ERR_STATE, "this rank has not been the destination of a gather");
+    *ptr = h->g_plane + (size_t)which * h->plan.Ny * h->plan.NzG;
+    return DFB_OK;
+}
+
+int dfb_gathered_to_host(dfb_handle h, int which, double* dst) {
+    if (!h || !dst || which < 0 || which > 4) return fail(DFB_ERR_ARG, "bad argument");
+    if (!h->g_plane) return fail(DFB_ERR_STATE, "this rank has not been the destination of a gather");
+    if (h->g_begun != h->g_ended) return fail(DFB_ERR_STATE, "a gather is outstanding: call dfb_gather_end first");
+    return guarded([&] {
+        CUDA_TRY(cudaSetDevice(h->device));
+        const size_t n = (size_t)h->plan.Ny * h->plan.NzG;
+        CUDA_TRY(cudaMemcpyAsync(dst, h->g_plane + (size_t)which * n, n * sizeof(double), cudaMemcpyDeviceToHost, h->comm_stream));
+        CUDA_TRY(cudaStreamSynchronize(h->comm_stream));
+    });
+}
+
+int dfb_gather_wire_bytes(dfb_handle h, int64_t* bytes) {
+    if (!h || !bytes) return fail(DFB_ERR_ARG, "bad argument");
+    *bytes = h->g_bytes_wire;
+    return DFB_OK;
+}
+
+int dfb_comm_destroy(dfb_handle h) {
+    if (!h) return fail(DFB_ERR_ARG, "handle is NULL");
+    return guarded([&] {
+        if (h->comm_stream) CUDA_TRY(cudaStreamSynchronize(h->comm_stream));
+        h->comm_release();
+        h->comm_rank = -1; h->comm_world = 0;
+    });
+}
+
+}  // extern "C"
+
+extern "C" {
 
 const char* dfb_last_error(void) { return g_last_error.c_str(); }
 const char* dfb_version(void) { return "dfb200 0.1 (sm_100a; rng spec v1)"; }

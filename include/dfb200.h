@@ -156,6 +156,29 @@ int dfb_scatter_to_cells(dfb_handle h, int which, int n, const int* plane_index,
                          const double* mean, double scale, double* dst);
 int dfb_sync(dfb_handle h);
 
+/* BASELINE config 4 -- ONE plane in spanwise slabs over the ranks of a job (one process per GPU, each with a handle created with its
+ * own k_begin/k_end; the filter itself needs no exchange, see k_begin).  NCCL over NVLink only hands the finished plane to the CFD rank
+ * (README.md:55 "MPI support to distribute result"; the consumer is the per-rank face loop of us3d_user.f90:85-92):
+ *   rank 0:     dfb_comm_unique_id(id)  -> ship the 128 bytes to every rank by the job's own means (MPI_Bcast, a file, ...)
+ *   every rank: dfb_comm_init(h, id, rank, world)            collective; checks that the slabs tile [0, Nz) in rank order
+ *   per step:   dfb_filter(h, dt); dfb_gather_begin(h, dst); [dfb_filter(h, dt) of the next step ...]; dfb_gather_end(h);
+ * dfb_gather_begin stages u', v', w' of the step just enqueued (the next dfb_filter may follow at once) and ships them -- 24 bytes per
+ * cell; T', rho' are row-wise multiples of u' (df.cpp:470-485) and are rebuilt on the destination, bit for bit -- on a communication
+ * stream; on the destination the slabs are assembled into row-major [Ny][Nz] planes.  dfb_gather_end blocks until that is done.
+ * A rank that only wants its own faces filled never gathers: it calls dfb_face_map + dfb_scatter_to_cells on its slab. */
+#define DFB_COMM_ID_BYTES 128
+int dfb_comm_unique_id(void* id128);
+int dfb_comm_init(dfb_handle h, const void* id128, int rank, int world);
+int dfb_comm_info(dfb_handle h, int* rank, int* world, int* bounds /* [2*world]: k_begin, k_end per rank; may be NULL */);
+int dfb_gather_begin(dfb_handle h, int dst_rank);
+int dfb_gather_end(dfb_handle h);
+/* destination rank: device pointer to / host copy of gathered field `which` (DFB_U_FLUC .. DFB_RHO_FLUC), [Ny][Nz_global] */
+int dfb_gathered_ptr(dfb_handle h, int which, void** ptr);
+int dfb_gathered_to_host(dfb_handle h, int which, double* dst);
+/* bytes this rank put on / took off the wire in the last dfb_gather_begin */
+int dfb_gather_wire_bytes(dfb_handle h, int64_t* bytes);
+int dfb_comm_destroy(dfb_handle h);
+
 /* noise injection ("ingest the reference's own draws").  Host arrays in the
  * reference's layouts: r_ys (Ny+2*Ny_max) x Nz (df.cpp:197); halo Ny x (2*Nz_max) = the left and
  * right Nz_max raw-noise columns of r_zs, the only part of it that is read (df.cpp:157,398). */
