@@ -1092,6 +1092,17 @@ int dfb_stream(dfb_handle h, void** stream) {
     return DFB_OK;
 }
 
+// page-lock / release a caller-owned host array so that the five copies of dfb_filter_to_host run at the PCIe rate
+// (the facades call these for their own std::vector / allocatable storage)
+int dfb_host_register(void* ptr, size_t bytes) {
+    if (!ptr || bytes == 0) return fail(DFB_ERR_ARG, "bad argument");
+    return guarded([&] { CUDA_TRY(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable)); });
+}
+int dfb_host_unregister(void* ptr) {
+    if (!ptr) return fail(DFB_ERR_ARG, "bad argument");
+    return guarded([&] { CUDA_TRY(cudaHostUnregister(ptr)); });
+}
+
 int dfb_sync(dfb_handle h) {
     if (!h) return fail(DFB_ERR_ARG, "handle is NULL");
     return guarded([&] { CUDA_TRY(cudaSetDevice(h->device)); CUDA_TRY(cudaStreamSynchronize(h->stream)); });
@@ -1604,6 +1615,23 @@ int dfb_filter_to_host_f(const dfb_handle* h, const double* dt, double* u, doubl
     return (h && dt) ? dfb_filter_to_host(*h, *dt, u, v, w, T, rho) : fail(DFB_ERR_ARG, "NULL argument");
 }
 int dfb_dims_f(const dfb_handle* h, int* Ny, int* Nz) { return h ? dfb_dims(*h, Ny, Nz) : fail(DFB_ERR_ARG, "NULL argument"); }
+int dfb_create_batch_f(const dfb_config* cfg, const int* nplanes, dfb_handle* out) {
+    return nplanes ? dfb_create_batch(cfg, *nplanes, out) : fail(DFB_ERR_ARG, "NULL argument");
+}
+int dfb_get_field_plane_f(const dfb_handle* h, const int* plane, const int* which, double* dst) {
+    return (h && plane && which) ? dfb_get_field_plane(*h, *plane, *which, dst, 0) : fail(DFB_ERR_ARG, "NULL argument");
+}
+int dfb_comm_init_f(const dfb_handle* h, const void* id128, const int* rank, const int* world) {
+    return (h && rank && world) ? dfb_comm_init(*h, id128, *rank, *world) : fail(DFB_ERR_ARG, "NULL argument");
+}
+int dfb_gather_begin_f(const dfb_handle* h, const int* dst_rank) { return (h && dst_rank) ? dfb_gather_begin(*h, *dst_rank) : fail(DFB_ERR_ARG, "NULL argument"); }
+int dfb_gather_end_f(const dfb_handle* h) { return h ? dfb_gather_end(*h) : fail(DFB_ERR_ARG, "NULL argument"); }
+int dfb_gathered_to_host_f(const dfb_handle* h, const int* which, double* dst) {
+    return (h && which) ? dfb_gathered_to_host(*h, *which, dst) : fail(DFB_ERR_ARG, "NULL argument");
+}
+int dfb_face_map_f(const dfb_handle* h, const int* n, const double* yf, const double* zf, int* plane_index) {
+    return (h && n) ? dfb_face_map(*h, *n, yf, zf, plane_index) : fail(DFB_ERR_ARG, "NULL argument");
+}
 int dfb_destroy_f(dfb_handle* h) {
     if (!h) return DFB_OK;
     int rc = dfb_destroy(*h);

@@ -155,6 +155,10 @@ int dfb_stream(dfb_handle h, void** stream);
 int dfb_scatter_to_cells(dfb_handle h, int which, int n, const int* plane_index, const int* dst_index,
                          const double* mean, double scale, double* dst);
 int dfb_sync(dfb_handle h);
+/* page-lock (cudaHostRegister) / release a caller-owned host array: dfb_filter_to_host into registered arrays runs at the PCIe
+ * rate; pageable arrays cost an extra staging pass inside the driver.  The C++ facade does this for its std::vectors. */
+int dfb_host_register(void* ptr, size_t bytes);
+int dfb_host_unregister(void* ptr);
 
 /* BASELINE config 4 -- ONE plane in spanwise slabs over the ranks of a job (one process per GPU, each with a handle created with its
  * own k_begin/k_end; the filter itself needs no exchange, see k_begin).  NCCL over NVLink only hands the finished plane to the CFD rank
@@ -238,6 +242,13 @@ int dfb_create_f(const dfb_config* cfg, dfb_handle* out);
 int dfb_filter_f(const dfb_handle* h, const double* dt);
 int dfb_filter_to_host_f(const dfb_handle* h, const double* dt, double* u, double* v, double* w, double* T, double* rho);
 int dfb_dims_f(const dfb_handle* h, int* Ny, int* Nz);
+int dfb_create_batch_f(const dfb_config* cfg, const int* nplanes, dfb_handle* out);
+int dfb_get_field_plane_f(const dfb_handle* h, const int* plane, const int* which, double* dst);
+int dfb_comm_init_f(const dfb_handle* h, const void* id128, const int* rank, const int* world);
+int dfb_gather_begin_f(const dfb_handle* h, const int* dst_rank);
+int dfb_gather_end_f(const dfb_handle* h);
+int dfb_gathered_to_host_f(const dfb_handle* h, const int* which, double* dst);
+int dfb_face_map_f(const dfb_handle* h, const int* n, const double* yf, const double* zf, int* plane_index);
 int dfb_destroy_f(dfb_handle* h);
 
 #ifdef __cplusplus

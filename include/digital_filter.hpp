@@ -16,10 +16,14 @@
 //     carrying on half-initialised (df.cpp:225-228, 492-495);
 //   * the per-stage public methods (generate_white_noise, filtering_sweeps, correlate_fields,
 //     apply_RST_scaling, get_rho_T_fluc; df.hpp:96-101) do not exist: the stages are fused on the GPU.
+//     get_rms() / plot_rms() / write_csv() / write_tecplot() (df.hpp:108-118) do: the reference's own driver calls get_rms()
+//     (test/cpp-main.cpp:17), and that file compiles unchanged against include/df/df.hpp.
+//   * the host vectors are page-locked (dfb_host_register) so that the five copies per filter() run at the PCIe rate;
 //   * the noise is the counter-based pcg32 stream of include/dfb_rng_spec.h (seedable, reproducible)
 //     instead of a random_device-seeded process-wide static (df.cpp:334).
 #pragma once
 #include <cstdint>
+#include <cstdio>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -29,6 +33,7 @@ typedef std::vector<double> Vector;
 
 struct FilterField {
     Vector filt, fluc;                 // Ny*Nz, row-major j*Nz + k  (df.hpp:28)
+    Vector rms_added, rms;             // df.hpp:27: filled by get_rms() (sums of squares on the device, df.cpp:571-582)
     std::vector<int> N_ys, N_zs;       // df.hpp:30
     double Lt = 0;                     // df.hpp:32
     int Nz_max = 0, Ny_max = 0;        // df.hpp:33
@@ -66,7 +71,10 @@ class DIGITAL_FILTER {
     explicit DIGITAL_FILTER(const DFConfigEx& cfg) { init(cfg); }
     DIGITAL_FILTER(const DIGITAL_FILTER&) = delete;
     DIGITAL_FILTER& operator=(const DIGITAL_FILTER&) = delete;
-    ~DIGITAL_FILTER() { if (h_) dfb_destroy(h_); }
+    ~DIGITAL_FILTER() {
+        for (void* p : pinned_) dfb_host_unregister(p);
+        if (h_) dfb_destroy(h_);
+    }
 
     // df.hpp:100, df.cpp:449-468
     void filter(double dt_input) {
@@ -86,6 +94,37 @@ class DIGITAL_FILTER {
         check(dfb_get_field(h_, DFB_T_FLUC, T_fluc_.data(), 0));
         check(dfb_get_field(h_, DFB_RHO_FLUC, rho_fluc_.data(), 0));
     }
+    // df.hpp:112, df.cpp:584-611 -- the reference's validation driver: 500 steps of dt = 1e-5 accumulating the squares of the five
+    // fields (here: on the device, in the z-sweep's epilogue), then plot_rms().  This is the call test/cpp-main.cpp:17 makes.
+    void get_rms() {
+        dt = 1e-5;
+        check(dfb_get_rms(h_, 500, dt));
+        FilterField* F[3] = {&u, &v, &w};
+        std::int64_t cnt = 0;
+        for (int f = 0; f < 3; ++f) {
+            F[f]->rms_added.assign(n_cells, 0.0); F[f]->rms.assign(n_cells, 0.0);
+            check(dfb_stats_get(h_, f, 0, F[f]->rms_added.data(), &cnt));
+            check(dfb_stats_get(h_, f, 1, F[f]->rms.data(), &cnt));
+        }
+        T_rms_.assign(n_cells, 0.0); rho_rms_.assign(n_cells, 0.0);
+        check(dfb_stats_get(h_, 3, 1, T_rms_.data(), &cnt));
+        check(dfb_stats_get(h_, 4, 1, rho_rms_.data(), &cnt));
+        rms_counter = (int)cnt;
+        fetch();                       // the fields of the last step, as the reference leaves them
+        plot_rms();
+    }
+    // df.hpp:113, df.cpp:613-675: writes ../files/cpp_vel_fluc_rms.csv and says so
+    void plot_rms() {
+        const std::string filename = "../files/cpp_vel_fluc_rms.csv";
+        check(dfb_write_rms_csv(h_, filename.c_str()));
+        std::printf("Finished plotting to file: %s\n", filename.c_str());
+    }
+    void write_csv(const std::string& filename) { check(dfb_write_csv(h_, filename.c_str())); std::printf("CSV written to %s\n", filename.c_str()); }   // df.cpp:764-803
+    void write_tecplot(const std::string& filename) { check(dfb_write_tecplot(h_, filename.c_str())); std::printf("Finished plotting.\n"); }           // df.cpp:712-762
+    const Vector& T_rms() const { return T_rms_; }
+    const Vector& rho_rms() const { return rho_rms_; }
+    int rms_counter = 0;               // df.hpp:63
+
     const Vector& T_fluc() const { return T_fluc_; }
     const Vector& rho_fluc() const { return rho_fluc_; }
     int get_Ny() const { return Ny; }
@@ -96,6 +135,8 @@ class DIGITAL_FILTER {
   private:
     int Ny = 0, Nz = 0, n_cells = 0;   // df.hpp:56
     Vector rho_fluc_, T_fluc_;         // df.hpp:59
+    Vector T_rms_, rho_rms_;           // df.hpp:84
+    std::vector<void*> pinned_;
     dfb_handle h_ = nullptr;
     bool fetch_ = true;
 
@@ -133,6 +174,10 @@ class DIGITAL_FILTER {
             check(dfb_info(h_, 1, f, &v64)); F[f]->Nz_max = (int)v64;
             F[f]->Lt = Lt[f];
         }
+        // page-lock what filter() copies into every step (a failure only costs speed: pageable copies still work)
+        Vector* out[5] = {&u.fluc, &v.fluc, &w.fluc, &T_fluc_, &rho_fluc_};
+        for (Vector* a : out)
+            if (!a->empty() && dfb_host_register(a->data(), a->size() * sizeof(double)) == DFB_OK) pinned_.push_back(a->data());
         if (c.noise_mode == DFB_NOISE_GENERATE) fetch();   // the constructor's first step (df.cpp:57-62)
     }
 };

@@ -50,6 +50,39 @@ int main(int argc, char** argv) {
     if (!(su > 0) || !isfinite(su) || !isfinite(sT)) return 7;
     printf("OK %d %d %.6f %.6f\n", Ny, Nz, sqrt(su / (double)n), sqrt(sT / (double)n));
     if (dfb_destroy_f(&h) != DFB_OK || h != NULL) return 8;
+
+    /* ---- create_digital_filter_batch / filter_batch (BASELINE config 5, the us3d_user.f90-style caller: create once, then one call
+     *      per timestep): arrays u(n_cells, nplanes) = [nplanes][n_cells] in C order, every scalar by reference ---- */
+    {
+        const int np = 3;
+        dfb_handle b = NULL;
+        c.plane_id = 10;
+        if (dfb_create_batch_f(&c, &np, &b) != DFB_OK) { fprintf(stderr, "create_batch: %s\n", dfb_last_error()); return 9; }
+        double *bu = malloc(8 * n * np), *bv = malloc(8 * n * np), *bw = malloc(8 * n * np), *bT = malloc(8 * n * np), *br = malloc(8 * n * np);
+        for (int s = 0; s < 2; ++s)
+            if (dfb_filter_to_host_f(&b, &dt, bu, bv, bw, bT, br) != DFB_OK) { fprintf(stderr, "filter_batch: %s\n", dfb_last_error()); return 10; }
+        /* plane 2 of the batch == a single-plane handle with plane_id 11, bit for bit */
+        dfb_handle one = NULL;
+        c.plane_id = 11;
+        if (dfb_create_f(&c, &one) != DFB_OK) return 11;
+        for (int s = 0; s < 2; ++s)
+            if (dfb_filter_to_host_f(&one, &dt, u, v, w, T, rho) != DFB_OK) return 12;
+        if (memcmp(u, bu + n, 8 * n) || memcmp(rho, br + n, 8 * n)) { fprintf(stderr, "batch plane differs from the single-plane handle\n"); return 13; }
+        const int plane = 2, which = DFB_W_FLUC;
+        if (dfb_get_field_plane_f(&b, &plane, &which, u) != DFB_OK || memcmp(u, bw + 2 * n, 8 * n)) return 14;
+        /* face_map: the centre of cell (j, k) maps to j*Nz + k */
+        double yv[2], zv[2];
+        double* tab = malloc(8 * (size_t)(Ny + Nz + 2));
+        if (dfb_get_table(one, 12, 0, tab, Ny + 1) != DFB_OK || dfb_get_table(one, 13, 0, tab + Ny + 1, Nz + 1) != DFB_OK) return 15;
+        const int jj = 17, kk = 123, nf = 2;
+        yv[0] = 0.5 * (tab[jj] + tab[jj + 1]); zv[0] = 0.5 * (tab[Ny + 1 + kk] + tab[Ny + 1 + kk + 1]);
+        yv[1] = tab[0]; zv[1] = tab[Ny + 1];
+        int cell[2];
+        if (dfb_face_map_f(&one, &nf, yv, zv, cell) != DFB_OK || cell[0] != jj * Nz + kk || cell[1] != 0) return 16;
+        printf("BATCH_OK %d\n", np);
+        free(tab); free(bu); free(bv); free(bw); free(bT); free(br);
+        dfb_destroy_f(&one); dfb_destroy_f(&b);
+    }
     free(u); free(v); free(w); free(T); free(rho);
     return 0;
 }
