@@ -97,6 +97,7 @@ def lib():
         L.dfb_gathered_to_host.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.dfb_gather_wire_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         L.dfb_comm_destroy.argtypes = [C.c_void_p]
+        L.dfb_comm_stream.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         for name in ("dfb_destroy", "dfb_sync", "dfb_first_step"):
             getattr(L, name).argtypes = [C.c_void_p]
         L.dfb_dims.argtypes = [C.c_void_p, c_ip, c_ip]
@@ -479,6 +480,11 @@ class DIGITAL_FILTER:
     def gathered_ptr(self, which):
         p = C.c_void_p()
         _check(lib().dfb_gathered_ptr(self._h, which, C.byref(p)))
+        return p.value
+
+    def comm_stream(self):
+        p = C.c_void_p()
+        _check(lib().dfb_comm_stream(self._h, C.byref(p)))
         return p.value
 
     def gather_wire_bytes(self):

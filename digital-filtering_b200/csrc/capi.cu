@@ -427,7 +427,11 @@ void build_device(dfb_filter_s& H) {
             std::vector<YRGroup> rg;
             std::vector<YRTile> rt;
             int wrows_max = 0;
-            for (int RB : {128, 64, 32}) {
+            int nbuf = 2;
+            const int trials[6][2] = {{128, 2}, {64, 2}, {32, 2}, {128, 1}, {64, 1}, {32, 1}};      // (rows per block, window buffers)
+            for (const auto& tr : trials) {
+                const int RB = tr[0];
+                nbuf = tr[1];
                 rg.clear(); rt.clear(); wrows_max = 0;
                 for (int f = 0; f < 3; ++f) {
                     const FieldPlan& FP = P.f[f];
@@ -464,10 +468,22 @@ void build_device(dfb_filter_s& H) {
                         for (int c0 = 0; c0 < D.f[f].We; c0 += YR_C) { t.col0 = c0; rt.push_back(t); }
                     }
                 }
-                if (ysweep_run_smem(wrows_max) <= (size_t)prop.sharedMemPerBlockOptin) { use_run = true; break; }
+                if (ysweep_run_smem(wrows_max, nbuf) <= (size_t)prop.sharedMemPerBlockOptin) { use_run = true; break; }
             }
-            // windows that do not fit even with 32-row blocks (N_y beyond ~190): the band-matrix kernels stream them
-            if (const char* ym = std::getenv("DFB_Y_MODE")) use_run = std::atoi(ym) == 2 && use_run;
+            // Two windows per CTA when they fit (N_y up to ~190 with 32-row blocks), else one (N_y up to ~400; the reference's default
+            // plane, N_y = 212, runs 128-row blocks this way); beyond that the band-matrix kernels stream the windows
+            // ... and only where it pays: where the half-width changes from row to row (the steep part of the reference's default
+            // plane: runs of one or two rows, N_y up to 212) a group of one row costs as much as the direct sum and the tall windows
+            // leave room for one buffer only -- measured there: 42 us against 32 us for the dense band matrices.  Run form when it
+            // executes less than half of the direct sum's multiply-adds and two windows fit; DFB_Y_MODE=2 forces it wherever it fits.
+            {
+                double c_run = 0, c_dense = 0;
+                for (const YRGroup& g : rg) c_run += 2.0 * (g.N + 1) + 4.0 * g.nrows;
+                for (int f = 0; f < 3; ++f) for (int v : P.f[f].N_y_row) c_dense += 2.0 * v + 1.0;
+                const bool fits = use_run;
+                use_run = fits && nbuf == 2 && c_run < 0.5 * c_dense;
+                if (const char* ym = std::getenv("DFB_Y_MODE")) use_run = std::atoi(ym) == 2 && fits;
+            }
             if (use_run) {
                 // most expensive tiles first; the persistent CTAs take them round-robin
                 auto cost = [&](const YRTile& t) { long long c = 0; for (int g = 0; g < t.ngroups; ++g) c += 2 * rg[t.g0 + g].N + 4 * rg[t.g0 + g].nrows + 8; return c; };
@@ -477,7 +493,8 @@ void build_device(dfb_filter_s& H) {
                 H.yp[0].rtiles = H.upload(rt);
                 H.yp[0].n_rtiles = (int)rt.size();
                 H.yp[0].r_wrows = wrows_max;
-                H.yp[0].r_smem = (int)ysweep_run_smem(wrows_max);
+                H.yp[0].r_nbuf = nbuf;
+                H.yp[0].r_smem = (int)ysweep_run_smem(wrows_max, nbuf);
                 H.yp[0].r_grid = prop.multiProcessorCount;
                 CUDA_TRY(ysweep_run_prepare((size_t)H.yp[0].r_smem));
             }
@@ -1585,6 +1602,13 @@ int dfb_gathered_to_host(dfb_handle h, int which, double* dst) {
         CUDA_TRY(cudaMemcpyAsync(dst, h->g_plane + (size_t)which * n, n * sizeof(double), cudaMemcpyDeviceToHost, h->comm_stream));
         CUDA_TRY(cudaStreamSynchronize(h->comm_stream));
     });
+}
+
+int dfb_comm_stream(dfb_handle h, void** stream) {
+    if (!h || !stream) return fail(DFB_ERR_ARG, "bad argument");
+    if (!h->comm) return fail(DFB_ERR_STATE, "dfb_comm_init has not been called");
+    *stream = h->comm_stream;
+    return DFB_OK;
 }
 
 int dfb_gather_wire_bytes(dfb_handle h, int64_t* bytes) {

@@ -137,6 +137,7 @@ struct YParams {
     int n_rtiles;              // > 0: the run-recursive kernel is the y-sweep of this handle
     int r_smem;                // its dynamic shared memory: control block + two window buffers
     int r_wrows;               // rows of one window buffer (largest window, whole boxes)
+    int r_nbuf;                // window buffers: 2, or 1 when two of the plane's tallest windows do not fit
     int r_grid;                // CTAs of the persistent grid (one per SM)
     int tile0;                 // first tile of this launch in `tiles` (dense tiles first, then recursive tiles)
     int n_tiles;               // tiles of this launch (dense kernel: walked with stride gridDim.x)

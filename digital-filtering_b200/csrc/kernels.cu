@@ -598,6 +598,7 @@ __global__ void __launch_bounds__(32 * (YR_CONSUMERS + 1), 1) ysweep_run_kernel(
     YRSmemCtl& ctl = *reinterpret_cast<YRSmemCtl*>(smem_raw);
     constexpr size_t CTL = (sizeof(YRSmemCtl) + 127) / 128 * 128;
     const size_t wbytes = (size_t)P.r_wrows * YR_C * sizeof(double);   // one window buffer (whole boxes)
+    const int nbuf = P.r_nbuf;                                         // 2: the next tile is staged while this one is computed; 1: windows too tall for two
     const int nP = P.D.P;
     const int n_all = P.n_rtiles * nP;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -618,8 +619,8 @@ __global__ void __launch_bounds__(32 * (YR_CONSUMERS + 1), 1) ysweep_run_kernel(
         if (lane == 0) {
             int i = 0;
             for (int tix = blockIdx.x; tix < n_all; tix += gridDim.x, ++i) {
-                const int s = i & 1;
-                if (i >= 2) mbar_wait(&ctl.empty[s], ((i >> 1) - 1) & 1);
+                const int s = i % nbuf;
+                if (i >= nbuf) mbar_wait(&ctl.empty[s], ((i / nbuf) - 1) & 1);
                 const YRTile t = P.rtiles[tix / nP];
                 const int pl = tix % nP;
                 ctl.tile[s] = t; ctl.plane[s] = pl; ctl.next_group[s] = YR_CONSUMERS;
@@ -639,8 +640,8 @@ __global__ void __launch_bounds__(32 * (YR_CONSUMERS + 1), 1) ysweep_run_kernel(
 
     int i = 0;
     for (int tix = blockIdx.x; tix < n_all; tix += gridDim.x, ++i) {
-        const int s = i & 1;
-        mbar_wait(&ctl.full[s], (i >> 1) & 1);
+        const int s = i % nbuf;
+        mbar_wait(&ctl.full[s], (i / nbuf) & 1);
         const YRTile& t = ctl.tile[s];
         const int pl = ctl.plane[s];
         const FieldDev& F = P.D.f[t.field];
@@ -756,10 +757,12 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
         ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
 }
 
-// Is the strip of a unit handled through the coalesced (piece-major) epilogue?  Whole strip inside the slab and 16-byte aligned.
+// Is the strip of a unit handled through the coalesced (piece-major) epilogue?  Its first cell 16-byte aligned and an even number of
+// its columns inside the slab (a partial last strip included): every 16-byte piece is then whole and aligned.
 __device__ __forceinline__ bool z_strip_coalesced(const ZParams& P, int j, int c0, int plane) {
     const size_t sbase = (size_t)plane * P.D.ps_cells + (size_t)j * P.D.W + c0;
-    return (c0 + 32 * P.zk <= P.D.W) && ((sbase & 1) == 0) && !(P.debug & 4);
+    const int cols = min(32 * P.zk, P.D.W - c0);
+    return ((cols & 1) == 0) && ((sbase & 1) == 0) && !(P.debug & 4);
 }
 
 __device__ __forceinline__ void z_issue_unit(const ZParams& P, const ZMaps& maps, const int* desc, int plane, void* buf, uint64_t* bar) {
@@ -774,7 +777,7 @@ __device__ __forceinline__ void z_issue_unit(const ZParams& P, const ZMaps& maps
     const int j = desc[0], c0 = desc[1], f = desc[2];
     const uint32_t cbytes = (uint32_t)desc[5];
     const bool fo = !P.S.first_step && z_strip_coalesced(P, j, c0, plane);
-    const uint32_t strip_bytes = 32u * (uint32_t)P.zk * 8u;
+    const uint32_t strip_bytes = (uint32_t)min(32 * P.zk, P.D.W - c0) * 8u;      // a partial last strip stages only what exists
     unsigned char* b = reinterpret_cast<unsigned char*>(buf);
     mbar_expect_tx(bar, (uint32_t)P.box_bytes + cbytes + (uint32_t)(ROWC * sizeof(double)) + (fo ? strip_bytes : 0u));
     tma_load_3d(b, &maps.m[f], 0, desc[4], plane * P.D.Ny + j, bar);
@@ -1061,9 +1064,11 @@ __global__ void __maxnreg__(MODE == 1 ? Z_REC_MAXNREG : 168) zsweep_epilogue_ker
                     const double2 cur = *gs;
                     *gs = make_double2(__dadd_rn(cur.x, __dmul_rn(x.x, y.x)), __dadd_rn(cur.y, __dmul_rn(x.y, y.y)));
                 };
+                const int npieces = min(32 * ZK, D.W - c0) >> 1;                            // 16-byte pieces of the strip inside the slab
 #pragma unroll
                 for (int m = 0; m < ZK / 2; ++m) {
                     const int pc = lane + 32 * m, r = pc / PPL;
+                    if (pc >= npieces) break;
                     double2 z = *reinterpret_cast<const double2*>(cbuf + r * LB + ((((pc % PPL) ^ swz(r))) << 4));
                     if (blend) {                                                                 // correlate_fields, df.cpp:415
                         const double2 fo = fo_t[pc];
@@ -1345,7 +1350,7 @@ cudaError_t launch_ysweep_tma(const YMaps& maps, const YParams& P, int n_dense, 
     return cudaSuccess;
 }
 
-size_t ysweep_run_smem(int wrows) { return (sizeof(YRSmemCtl) + 127) / 128 * 128 + (size_t)2 * wrows * YR_C * sizeof(double); }
+size_t ysweep_run_smem(int wrows, int nbuf) { return (sizeof(YRSmemCtl) + 127) / 128 * 128 + (size_t)nbuf * wrows * YR_C * sizeof(double); }
 
 cudaError_t ysweep_run_prepare(size_t smem) {
     cudaError_t e = cudaFuncSetAttribute(ysweep_run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

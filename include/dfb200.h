@@ -179,6 +179,8 @@ int dfb_gather_end(dfb_handle h);
 /* destination rank: device pointer to / host copy of gathered field `which` (DFB_U_FLUC .. DFB_RHO_FLUC), [Ny][Nz_global] */
 int dfb_gathered_ptr(dfb_handle h, int which, void** ptr);
 int dfb_gathered_to_host(dfb_handle h, int which, double* dst);
+/* the cudaStream_t the hand-off runs on (for device-side timing of it) */
+int dfb_comm_stream(dfb_handle h, void** stream);
 /* bytes this rank put on / took off the wire in the last dfb_gather_begin */
 int dfb_gather_wire_bytes(dfb_handle h, int64_t* bytes);
 int dfb_comm_destroy(dfb_handle h);
