@@ -335,6 +335,10 @@ def slab_job(dfb, torch, dist, rank, world, local, steps=20):
                     sf.filter(DT)
                     sf.gather_begin()
                     sf.gather_end()
+            elif mode == 3:                                # the hand-off alone (staging + transfer + assembly of the same step again and again)
+                for _ in range(n):
+                    sf.gather_begin()
+                    sf.gather_end()
             else:
                 sf.filter(DT)
                 sf.gather_begin()
@@ -356,7 +360,7 @@ def slab_job(dfb, torch, dist, rank, world, local, steps=20):
         fence()
         return reduce_max(a.elapsed_time(b)) / steps
 
-    t_no, t_sync, t_ovl = timed(0), timed(1), timed(2)
+    t_no, t_sync, t_ovl, t_gather = timed(0), timed(1), timed(2), timed(3)
     wire = torch.tensor([float(sf.filt.gather_wire_bytes()) if rank != 0 else 0.0], dtype=torch.float64, device=dev)
     dist.all_reduce(wire, op=dist.ReduceOp.SUM)
     # slab == whole: the plane gathered now against the same plane filtered whole on rank 0's GPU (same number of steps)
@@ -380,11 +384,14 @@ def slab_job(dfb, torch, dist, rank, world, local, steps=20):
         whole.close()
         cells = plane["Ny"] * plane["Nz"]
         rec = dict(workload=plane["name"], n_gpus=world, slabs=[list(b) for b in sf.bounds], steps=steps,
-                   ms_per_step_no_gather=t_no, ms_per_step_with_gather=t_sync, ms_per_step_with_gather_overlapped=t_ovl,
+                   ms_per_step_no_gather=t_no, ms_per_step_with_gather=t_sync, ms_per_step_with_gather_overlapped=t_ovl, ms_gather_alone=t_gather,
                    one_gpu_ms_per_step=one_gpu_ms, speedup_no_gather=one_gpu_ms / t_no, speedup_with_gather_overlapped=one_gpu_ms / t_ovl,
                    cell_updates_per_s_with_gather_overlapped=cells / (t_ovl * 1e-3),
                    wire_bytes_per_step=int(wire.item()), wire_bytes_per_cell=24, gathered_equals_whole_plane_bitwise=bool(same),
-                   transport="NCCL send/recv inside libdfb200.so (dfb_gather_begin/_end); u', v', w' on the wire, T', rho' rebuilt on rank 0",
+                   transport={2: "peer-to-peer inside libdfb200.so (dfb_gather_begin/_end): CUDA IPC mapping of rank 0's plane, each sender's copy engine writes "
+                                 "u', v', w' of its slab into the final layout over NVLink, stream memory operations order it; T', rho' rebuilt on rank 0",
+                              1: "NCCL send/recv inside libdfb200.so (dfb_gather_begin/_end) + assembly kernel; u', v', w' on the wire, T', rho' rebuilt on rank 0"}.get(int(sf.filt.info(12)), "?"),
+                   wire_gbs_gather_alone=wire.item() / (t_gather * 1e-3) / 1e9,
                    timing="CUDA events on the library's compute and communication streams, max over ranks")
     dist.barrier()
     sf.filt.close()

@@ -9,6 +9,8 @@
 #include <memory>
 #include <string>
 #include <vector>
+#include <chrono>
+#include <thread>
 #include <nccl.h>
 #include "dfb200.h"
 #include "plan.hpp"
@@ -96,12 +98,24 @@ struct dfb_filter_s {
     ncclComm_t comm = nullptr;
     int comm_rank = -1, comm_world = 0;
     std::vector<int> comm_bounds;     // [2*world]: k_begin, k_end of every rank
-    cudaStream_t comm_stream = nullptr;
+    cudaStream_t comm_stream = nullptr;   // NCCL transfers
+    cudaStream_t asm_stream = nullptr;    // destination rank: assembly of a slab while the next one is on the wire
+    cudaEvent_t ev_slab[16] = {};         // slab of rank r has landed (comm_stream)
     double* g_send = nullptr;         // staged u', v', w' of this slab: [3][Ny][W]
     double* g_recv = nullptr;         // dst rank: every rank's staged slab back to back, [rank][3][Ny][W_rank]
     double* g_plane = nullptr;        // dst rank: the assembled plane, [5][Ny][NzG]
     std::vector<size_t> g_recv_off;   // offsets (doubles) of the ranks' slabs in g_recv
     cudaEvent_t ev_gstaged = nullptr, ev_gdone = nullptr;
+    // peer-to-peer transport of the hand-off (default; NCCL send/recv when CUDA IPC is not available between the ranks):
+    // the destination's plane and every rank's flag block are mapped into the other ranks through CUDA IPC; a sender's copy
+    // engine writes its slab straight into the plane's final layout over NVLink, flags (stream memory operations) order it
+    int transport = 0;                // 0 none yet, 1 NCCL send/recv + assembly, 2 peer-to-peer copies
+    unsigned long long* flags = nullptr;          // this rank's flag block: [r] = last gather whose slab of rank r has landed here; [32] = last gather this rank may write for
+    unsigned long long* peer_flags[16] = {};      // the other ranks' flag blocks
+    double* peer_plane = nullptr;     // the destination's g_plane as mapped here
+    int peer_plane_of = -1;
+    unsigned long long* seq_ring = nullptr;       // pinned host ring of gather sequence numbers (sources of the 8-byte flag copies)
+    unsigned long long g_seq = 0;
     int g_dst = -1;
     int64_t g_begun = 0, g_ended = 0, g_bytes_wire = 0;
     bool g_after_first_only = false;  // the gathered step was the constructor's: T', rho' are zero (df.cpp:57-65)
@@ -134,6 +148,11 @@ struct dfb_filter_s {
         for (int b = 0; b < 2; ++b) { if (ev_noise[b]) cudaEventDestroy(ev_noise[b]); if (ev_free[b]) cudaEventDestroy(ev_free[b]); }
         for (int q = 0; q < 2; ++q) { if (ev_staged[q]) cudaEventDestroy(ev_staged[q]); if (ev_copied[q]) cudaEventDestroy(ev_copied[q]); }
         if (comm_stream) cudaStreamSynchronize(comm_stream);
+        if (asm_stream) { cudaStreamSynchronize(asm_stream); cudaStreamDestroy(asm_stream); }
+        for (auto& e : ev_slab) if (e) cudaEventDestroy(e);
+        for (auto& pf : peer_flags) if (pf) cudaIpcCloseMemHandle(pf);
+        if (peer_plane) cudaIpcCloseMemHandle(peer_plane);
+        if (seq_ring) cudaFreeHost(seq_ring);
         if (ev_gstaged) cudaEventDestroy(ev_gstaged);
         if (ev_gdone) cudaEventDestroy(ev_gdone);
         comm_release();
@@ -158,6 +177,19 @@ EncodeTiledFn encode_tiled() {
         CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
         if (q != cudaDriverEntryPointSuccess || !p) throw Error{DFB_ERR_CUDA, "cuTensorMapEncodeTiled not available"};
         fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+typedef CUresult (*StreamWaitValue64Fn)(CUstream, CUdeviceptr, cuuint64_t, unsigned int);
+StreamWaitValue64Fn stream_wait_value64() {
+    static StreamWaitValue64Fn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        CUDA_TRY(cudaGetDriverEntryPoint("cuStreamWaitValue64", &p, cudaEnableDefault, &q));
+        if (q != cudaDriverEntryPointSuccess || !p) throw Error{DFB_ERR_CUDA, "cuStreamWaitValue64 not available"};
+        fn = reinterpret_cast<StreamWaitValue64Fn>(p);
     }
     return fn;
 }
@@ -950,6 +982,7 @@ int dfb_info(dfb_handle h, int what, int field, int64_t* out64) {
         case 8: *out64 = h->tuned ? h->n_tiles_rec : 0; break;
         case 9: *out64 = h->tuned ? h->n_tiles_dense : 0; break;
         case 10: *out64 = h->tuned ? h->y_form : -1; break;
+        case 12: *out64 = h->transport; break;
         case 11: *out64 = h->tuned ? h->yp[0].n_rtiles : 0; break;
         default: return fail(DFB_ERR_ARG, "unknown info selector");
     }
@@ -1465,6 +1498,70 @@ void dfb_filter_s::comm_release() {
     if (comm) { try { nccl().CommDestroy(comm); } catch (...) {} comm = nullptr; }
 }
 
+
+namespace {
+
+// Peer-to-peer hand-off of one step (transport 2).  seq = number of this gather (the same on every rank: the call is collective).
+//   destination: tells every sender "the plane is free for gather seq" (8-byte copy into the sender's flag block), assembles its own
+//                slab, then per sender waits -- a stream memory operation, no SM involved -- for "slab of gather seq landed" and
+//                rebuilds T', rho' of that slab's columns from the u' that just arrived;
+//   sender:      waits for "plane free", lets its copy engine write u', v', w' of its slab straight into the plane's final row-major
+//                layout over NVLink (three strided 2-D copies: 24 bytes per cell on the wire, no SM, no staging on the far side),
+//                then raises "slab landed" on the destination.
+void gather_p2p(dfb_filter_s& H, int dst_rank, int first_only) {
+    const int Ny = H.plan.Ny, NzG = H.plan.NzG, world = H.comm_world, me = H.comm_rank;
+    const size_t n = H.D[0].ps_cells, np = (size_t)Ny * NzG;
+    const int W = H.D[0].W, k0 = H.plan.k0;
+    const bool dst = me == dst_rank;
+    // (re)map the destination's plane: collective, only when the destination changes
+    if (H.peer_plane_of != dst_rank) {
+        struct Rec { cudaIpcMemHandle_t hd; int ok; int pad[3]; };
+        Rec mine{};
+        if (dst) mine.ok = cudaIpcGetMemHandle(&mine.hd, H.g_plane) == cudaSuccess ? 1 : 0;
+        Rec* dr = reinterpret_cast<Rec*>(H.dalloc<unsigned char>(sizeof(Rec) * (size_t)(world + 1)));
+        CUDA_TRY(cudaMemcpyAsync(dr, &mine, sizeof(Rec), cudaMemcpyHostToDevice, H.comm_stream));
+        NCCL_TRY(nccl().AllGather(dr, dr + 1, sizeof(Rec), ncclUint8, H.comm, H.comm_stream));
+        std::vector<Rec> recs((size_t)world);
+        CUDA_TRY(cudaMemcpyAsync(recs.data(), dr + 1, sizeof(Rec) * (size_t)world, cudaMemcpyDeviceToHost, H.comm_stream));
+        CUDA_TRY(cudaStreamSynchronize(H.comm_stream));
+        if (!recs[dst_rank].ok) throw Error{DFB_ERR_CUDA, "the destination rank could not export its plane through CUDA IPC"};
+        if (H.peer_plane) { cudaIpcCloseMemHandle(H.peer_plane); H.peer_plane = nullptr; }
+        if (!dst) {
+            void* p = nullptr;
+            CUDA_TRY(cudaIpcOpenMemHandle(&p, recs[dst_rank].hd, cudaIpcMemLazyEnablePeerAccess));
+            H.peer_plane = static_cast<double*>(p);
+        }
+        H.peer_plane_of = dst_rank;
+    }
+    const unsigned long long seq = ++H.g_seq;
+    unsigned long long* src = H.seq_ring + (seq % 64);      // pinned: the 8-byte flag copies below are truly asynchronous
+    *src = seq;
+    if (dst) {
+        for (int r = 0; r < world; ++r)
+            if (r != me) CUDA_TRY(cudaMemcpyAsync(H.peer_flags[r] + 32, src, 8, cudaMemcpyHostToDevice, H.asm_stream));   // "plane free for seq"
+        // own slab: staged in g_recv (see dfb_gather_begin) -> plane, with T', rho'
+        CUDA_TRY(launch_assemble(H.g_recv + H.g_recv_off[me], H.g_plane, H.D[0].rowc, Ny, NzG, k0, W, first_only, H.comm_stream));
+        for (int r = 0; r < world; ++r) {
+            if (r == me) continue;
+            CUresult cr = stream_wait_value64()(H.comm_stream, (CUdeviceptr)(uintptr_t)(H.flags + r), seq, CU_STREAM_WAIT_VALUE_GEQ);
+            if (cr != CUDA_SUCCESS) throw Error{DFB_ERR_CUDA, "cuStreamWaitValue64 failed (" + std::to_string((int)cr) + ")"};
+            const int rk0 = H.comm_bounds[2 * r], rW = H.comm_bounds[2 * r + 1] - rk0;
+            CUDA_TRY(launch_rebuild(H.g_plane, H.D[0].rowc, Ny, NzG, rk0, rW, first_only, H.comm_stream));
+            H.g_bytes_wire += (int64_t)3 * Ny * rW * 8;
+        }
+    } else {
+        CUresult cr = stream_wait_value64()(H.comm_stream, (CUdeviceptr)(uintptr_t)(H.flags + 32), seq, CU_STREAM_WAIT_VALUE_GEQ);
+        if (cr != CUDA_SUCCESS) throw Error{DFB_ERR_CUDA, "cuStreamWaitValue64 failed (" + std::to_string((int)cr) + ")"};
+        for (int f = 0; f < 3; ++f)
+            CUDA_TRY(cudaMemcpy2DAsync(H.peer_plane + (size_t)f * np + k0, (size_t)NzG * 8, H.g_send + (size_t)f * n, (size_t)W * 8, (size_t)W * 8, (size_t)Ny,
+                                       cudaMemcpyDeviceToDevice, H.comm_stream));
+        CUDA_TRY(cudaMemcpyAsync(H.peer_flags[dst_rank] + me, src, 8, cudaMemcpyHostToDevice, H.comm_stream));             // "slab of rank me landed"
+        H.g_bytes_wire = (int64_t)3 * n * 8;
+    }
+}
+
+}  // namespace
+
 extern "C" {
 
 int dfb_comm_unique_id(void* id128) {
@@ -1483,9 +1580,15 @@ int dfb_comm_init(dfb_handle h, const void* id128, int rank, int world) {
         std::memcpy(&id, id128, sizeof(id));
         NCCL_TRY(nccl().CommInitRank(&h->comm, world, id, rank));
         h->comm_rank = rank; h->comm_world = world;
-        CUDA_TRY(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
-        CUDA_TRY(cudaEventCreateWithFlags(&h->ev_gstaged, cudaEventDisableTiming));
-        CUDA_TRY(cudaEventCreateWithFlags(&h->ev_gdone, cudaEventDisableTiming));
+        if (world > 16) throw Error{DFB_ERR_ARG, "at most 16 ranks per plane"};
+        // the transfer / assembly streams get the highest priority: their (small) kernels go first whenever an SM has room
+        {
+            int prio_lo = 0, prio_hi = 0;
+            CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+            CUDA_TRY(cudaStreamCreateWithPriority(&h->comm_stream, cudaStreamNonBlocking, prio_hi));
+            CUDA_TRY(cudaStreamCreateWithPriority(&h->asm_stream, cudaStreamNonBlocking, prio_hi));
+            for (int r = 0; r < world; ++r) CUDA_TRY(cudaEventCreateWithFlags(&h->ev_slab[r], cudaEventDisableTiming));
+        }
         // every rank learns every rank's slab: one all-gather of (k_begin, k_end, Ny, Nz_global)
         int mine[4] = {h->plan.k0, h->plan.k1, h->plan.Ny, h->plan.NzG};
         int* d = h->dalloc<int>((size_t)4 * (world + 1));
@@ -1506,6 +1609,58 @@ int dfb_comm_init(dfb_handle h, const void* id128, int rank, int world) {
         if (h->comm_bounds[0] != 0 || h->comm_bounds[2 * world - 1] != h->plan.NzG)
             throw Error{DFB_ERR_ARG, "slabs must cover [0, Nz)"};
         h->g_send = h->dalloc<double>((size_t)3 * h->D[0].ps_cells, false);
+
+        // ---- peer-to-peer transport: every rank exports a flag block through CUDA IPC; all ranks must succeed, else NCCL send/recv ----
+        h->transport = 1;
+        const char* tr = std::getenv("DFB_GATHER_TRANSPORT");
+        if (world > 1 && !(tr && std::strcmp(tr, "nccl") == 0)) {
+            struct Rec { cudaIpcMemHandle_t hd; int ok; int pad[3]; };
+            static_assert(sizeof(Rec) % 8 == 0, "");
+            Rec mine{};
+            h->flags = h->dalloc<unsigned long long>(64);
+            CUDA_TRY(cudaStreamSynchronize(h->stream));
+            mine.ok = cudaIpcGetMemHandle(&mine.hd, h->flags) == cudaSuccess ? 1 : 0;
+            if (mine.ok && cudaHostAlloc(reinterpret_cast<void**>(&h->seq_ring), 64 * sizeof(unsigned long long), cudaHostAllocPortable) != cudaSuccess) mine.ok = 0;
+            cudaGetLastError();
+            Rec* dr = reinterpret_cast<Rec*>(h->dalloc<unsigned char>(sizeof(Rec) * (size_t)(world + 1)));
+            CUDA_TRY(cudaMemcpyAsync(dr, &mine, sizeof(Rec), cudaMemcpyHostToDevice, h->comm_stream));
+            NCCL_TRY(nccl().AllGather(dr, dr + 1, sizeof(Rec), ncclUint8, h->comm, h->comm_stream));
+            std::vector<Rec> recs((size_t)world);
+            CUDA_TRY(cudaMemcpyAsync(recs.data(), dr + 1, sizeof(Rec) * (size_t)world, cudaMemcpyDeviceToHost, h->comm_stream));
+            CUDA_TRY(cudaStreamSynchronize(h->comm_stream));
+            int ok = 1;
+            for (int r = 0; r < world; ++r) ok &= recs[r].ok;
+            for (int r = 0; ok && r < world; ++r) {
+                if (r == rank) continue;
+                void* p = nullptr;
+                if (cudaIpcOpenMemHandle(&p, recs[r].hd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); break; }
+                h->peer_flags[r] = static_cast<unsigned long long*>(p);
+            }
+            // second round: did every rank manage to map every other rank?
+            int* dok = h->dalloc<int>((size_t)world + 1);
+            CUDA_TRY(cudaMemcpyAsync(dok, &ok, sizeof(int), cudaMemcpyHostToDevice, h->comm_stream));
+            NCCL_TRY(nccl().AllGather(dok, dok + 1, 1, ncclInt32, h->comm, h->comm_stream));
+            std::vector<int> oks((size_t)world);
+            CUDA_TRY(cudaMemcpyAsync(oks.data(), dok + 1, sizeof(int) * (size_t)world, cudaMemcpyDeviceToHost, h->comm_stream));
+            CUDA_TRY(cudaStreamSynchronize(h->comm_stream));
+            for (int v : oks) ok &= v;
+            if (ok) { h->transport = 2; (void)stream_wait_value64(); }
+        }
+        // The sweeps are persistent kernels that fill every SM (and all of its shared memory): an NCCL transfer kernel launched beside
+        // them only starts at their kernel boundaries.  With the NCCL transport the persistent grids therefore leave a few SMs free
+        // (DFB_COMM_SMS, default 8 of 148); the peer-to-peer transport moves the data with the copy engines and needs none.
+        {
+            cudaDeviceProp prop;
+            CUDA_TRY(cudaGetDeviceProperties(&prop, h->device));
+            const int reserve = std::getenv("DFB_COMM_SMS") ? std::atoi(std::getenv("DFB_COMM_SMS")) : (h->transport == 2 ? 0 : 8);
+            const int sms = std::max(1, prop.multiProcessorCount - std::max(0, reserve));
+            if (world > 1 && h->tuned)
+                for (int b = 0; b < 2; ++b) {
+                    if (h->yp[b].r_grid > sms) h->yp[b].r_grid = sms;
+                    const int per_sm = std::max(1, h->zp[b].nblocks / prop.multiProcessorCount);
+                    if (h->zp[b].nblocks > per_sm * sms) h->zp[b].nblocks = per_sm * sms;
+                }
+        }
     });
 }
 
@@ -1543,31 +1698,38 @@ int dfb_gather_begin(dfb_handle h, int dst_rank) {
         // fields as soon as this copy is done); the wire carries these 24 bytes per cell -- T', rho' are row-wise multiples of u'
         // (df.cpp:470-485) and are rebuilt on the destination
         double* stage = dst ? h->g_recv + h->g_recv_off[h->comm_rank] : h->g_send;
-        CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_gdone, 0));        // the previous gather has shipped the staging buffer
+        CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_gdone, 0));        // the previous gather has shipped / assembled the staging buffer
         for (int f = 0; f < 3; ++f)
             CUDA_TRY(cudaMemcpyAsync(stage + (size_t)f * n, field_ptr(*h, f), n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
         CUDA_TRY(cudaEventRecord(h->ev_gstaged, h->stream));
         CUDA_TRY(cudaStreamWaitEvent(h->comm_stream, h->ev_gstaged, 0));
         h->g_bytes_wire = 0;
-        if (world > 1) {
-            NCCL_TRY(nccl().GroupStart());
-            if (dst) {
-                for (int r = 0; r < world; ++r) {
-                    if (r == dst_rank) continue;
-                    const size_t cnt = h->g_recv_off[r + 1] - h->g_recv_off[r];
-                    NCCL_TRY(nccl().Recv(h->g_recv + h->g_recv_off[r], cnt, ncclDouble, r, h->comm, h->comm_stream));
-                    h->g_bytes_wire += (int64_t)cnt * 8;
-                }
-            } else {
-                NCCL_TRY(nccl().Send(h->g_send, 3 * n, ncclDouble, dst_rank, h->comm, h->comm_stream));
-                h->g_bytes_wire = (int64_t)3 * n * 8;
+        const int first_only = h->g_after_first_only ? 1 : 0;
+        if (h->transport == 2 && world > 1) {
+            gather_p2p(*h, dst_rank, first_only);
+        } else if (dst) {
+            // [rank][3][Ny][W_rank] -> row-major planes u', v', w' + T', rho' rebuilt with the row constants (bitwise what the slabs
+            // hold).  The slabs are received one after the other (each sender alone fills this GPU's NVLink ingress) and assembled
+            // on a second stream as they land: the assembly of rank r runs under the transfer of rank r+1.
+            auto assemble = [&](int r) {
+                CUDA_TRY(cudaEventRecord(h->ev_slab[r], h->comm_stream));
+                CUDA_TRY(cudaStreamWaitEvent(h->asm_stream, h->ev_slab[r], 0));
+                CUDA_TRY(launch_assemble(h->g_recv + h->g_recv_off[r], h->g_plane, h->D[0].rowc, Ny, NzG, h->comm_bounds[2 * r],
+                                         h->comm_bounds[2 * r + 1] - h->comm_bounds[2 * r], first_only, h->asm_stream));
+            };
+            assemble(h->comm_rank);                                        // this rank's own slab: staged above
+            for (int r = 0; r < world; ++r) {
+                if (r == dst_rank) continue;
+                const size_t cnt = h->g_recv_off[r + 1] - h->g_recv_off[r];
+                NCCL_TRY(nccl().Recv(h->g_recv + h->g_recv_off[r], cnt, ncclDouble, r, h->comm, h->comm_stream));
+                h->g_bytes_wire += (int64_t)cnt * 8;
+                assemble(r);
             }
-            NCCL_TRY(nccl().GroupEnd());
-        }
-        if (dst) {
-            // [rank][3][Ny][W_rank] -> row-major planes u', v', w' + T', rho' rebuilt with the row constants (bitwise what the slabs hold)
-            std::vector<int> b(h->comm_bounds);
-            CUDA_TRY(launch_assemble(h->g_recv, h->g_plane, h->D[0].rowc, Ny, NzG, world, b.data(), h->g_after_first_only ? 1 : 0, h->comm_stream));
+            CUDA_TRY(cudaEventRecord(h->ev_slab[dst_rank], h->asm_stream));    // everything assembled
+            CUDA_TRY(cudaStreamWaitEvent(h->comm_stream, h->ev_slab[dst_rank], 0));
+        } else {
+            NCCL_TRY(nccl().Send(h->g_send, 3 * n, ncclDouble, dst_rank, h->comm, h->comm_stream));
+            h->g_bytes_wire = (int64_t)3 * n * 8;
         }
         CUDA_TRY(cudaEventRecord(h->ev_gdone, h->comm_stream));
         h->g_begun += 1;
@@ -1580,7 +1742,17 @@ int dfb_gather_end(dfb_handle h) {
     if (h->g_begun == h->g_ended) return fail(DFB_ERR_STATE, "no dfb_gather_begin is outstanding");
     return guarded([&] {
         CUDA_TRY(cudaSetDevice(h->device));
-        CUDA_TRY(cudaEventSynchronize(h->ev_gdone));
+        // bounded wait: a rank that died would otherwise leave this one blocked for ever on a flag that never comes
+        const double limit = std::getenv("DFB_GATHER_TIMEOUT_S") ? std::atof(std::getenv("DFB_GATHER_TIMEOUT_S")) : 120.0;
+        const auto t0 = std::chrono::steady_clock::now();
+        for (;;) {
+            cudaError_t q = cudaEventQuery(h->ev_gdone);
+            if (q == cudaSuccess) break;
+            if (q != cudaErrorNotReady) CUDA_TRY(q);
+            if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > limit)
+                throw Error{DFB_ERR_STATE, "dfb_gather_end: the hand-off did not complete within the time limit (a rank of the job is missing?)"};
+            std::this_thread::yield();
+        }
         h->g_ended += 1;
     });
 }

@@ -1192,21 +1192,16 @@ __global__ void __launch_bounds__(256) scatter_kernel(const double* __restrict__
     dst[d] = __fma_rn(scale, field[c], base);
 }
 
-// config 4, destination rank: the ranks' staged slabs [rank][3][Ny][W_rank] -> row-major planes [5][Ny][NzG]; T' and rho' are
-// rebuilt from u' with the row constants, with the epilogue's own roundings (df.cpp:474-481), so the assembled plane is bit for
-// bit what the slabs hold.  bounds = k_begin/k_end per rank (<= 16 ranks, by value).
-struct AsmBounds { int k[34]; };
-__global__ void __launch_bounds__(256) assemble_kernel(const double* __restrict__ recv, double* __restrict__ plane, const double* __restrict__ rowc,
-                                                       int Ny, int NzG, int world, AsmBounds B, int first_only) {
+// config 4, destination rank: ONE rank's staged slab [3][Ny][W] -> its columns [k0, k0+W) of the row-major planes [5][Ny][NzG];
+// T' and rho' are rebuilt from u' with the row constants, with the epilogue's own roundings (df.cpp:474-481), so the assembled
+// plane is bit for bit what the slabs hold.  Launched per source rank as its slab lands (the next rank's transfer runs meanwhile).
+__global__ void __launch_bounds__(256) assemble_kernel(const double* __restrict__ slab, double* __restrict__ plane, const double* __restrict__ rowc,
+                                                       int Ny, int NzG, int k0, int W, int first_only) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y;
-    if (k >= NzG) return;
-    int r = 0;
-    size_t off = 0;
-    while (r + 1 < world && k >= B.k[2 * r + 1]) { off += (size_t)3 * Ny * (B.k[2 * r + 1] - B.k[2 * r]); ++r; }
-    const int W = B.k[2 * r + 1] - B.k[2 * r];
-    const size_t cell = (size_t)j * W + (k - B.k[2 * r]), nslab = (size_t)Ny * W, n = (size_t)Ny * NzG, idx = (size_t)j * NzG + k;
-    const double u = recv[off + cell], v = recv[off + nslab + cell], w = recv[off + 2 * nslab + cell];
+    if (k >= W) return;
+    const size_t cell = (size_t)j * W + k, nslab = (size_t)Ny * W, n = (size_t)Ny * NzG, idx = (size_t)j * NzG + k0 + k;
+    const double u = __ldcs(slab + cell), v = __ldcs(slab + nslab + cell), w = __ldcs(slab + 2 * nslab + cell);
     plane[idx] = u; plane[n + idx] = v; plane[2 * n + idx] = w;
     double T = 0.0, rho = 0.0;
     if (!first_only) {
@@ -1218,12 +1213,31 @@ __global__ void __launch_bounds__(256) assemble_kernel(const double* __restrict_
     plane[3 * n + idx] = T; plane[4 * n + idx] = rho;
 }
 
-cudaError_t launch_assemble(const double* recv, double* plane, const double* rowc, int Ny, int NzG, int world, const int* bounds, int first_only,
-                            cudaStream_t st) {
-    if (world > 16) return cudaErrorInvalidValue;
-    AsmBounds B{};
-    for (int i = 0; i < 2 * world; ++i) B.k[i] = bounds[i];
-    assemble_kernel<<<dim3((unsigned)((NzG + 255) / 256), (unsigned)Ny), 256, 0, st>>>(recv, plane, rowc, Ny, NzG, world, B, first_only);
+// config 4, peer-to-peer transport, destination rank: u', v', w' of the columns [k0, k0+W) have just been written into the planes by
+// the owning rank's copy engine; rebuild T', rho' of those columns from u' (same roundings as the epilogue, df.cpp:474-481).
+__global__ void __launch_bounds__(256) rebuild_kernel(double* __restrict__ plane, const double* __restrict__ rowc, int Ny, int NzG, int k0, int W,
+                                                      int first_only) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (k >= W) return;
+    const size_t n = (size_t)Ny * NzG, idx = (size_t)j * NzG + k0 + k;
+    double T = 0.0, rho = 0.0;
+    if (!first_only) {
+        const double* rc = rowc + (size_t)j * ROWC;
+        const double t2 = __dmul_rn(rc[4], plane[idx]);
+        T = __dmul_rn(t2, rc[5]);
+        rho = __dmul_rn(-t2, rc[6]);
+    }
+    plane[3 * n + idx] = T; plane[4 * n + idx] = rho;
+}
+
+cudaError_t launch_rebuild(double* plane, const double* rowc, int Ny, int NzG, int k0, int W, int first_only, cudaStream_t st) {
+    rebuild_kernel<<<dim3((unsigned)((W + 255) / 256), (unsigned)Ny), 256, 0, st>>>(plane, rowc, Ny, NzG, k0, W, first_only);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_assemble(const double* slab, double* plane, const double* rowc, int Ny, int NzG, int k0, int W, int first_only, cudaStream_t st) {
+    assemble_kernel<<<dim3((unsigned)((W + 255) / 256), (unsigned)Ny), 256, 0, st>>>(slab, plane, rowc, Ny, NzG, k0, W, first_only);
     return cudaGetLastError();
 }
 

@@ -23,8 +23,8 @@ cudaError_t launch_zsweep_tuned(const ZMaps& maps, const ZParams& P, cudaStream_
 cudaError_t launch_stats(const PlaneDev& D, double* sums, cudaStream_t st);
 cudaError_t launch_scatter(const double* field, int n, const int* plane_index, const int* dst_index, const double* mean, double scale,
                            double* dst, cudaStream_t st);
-cudaError_t launch_assemble(const double* recv, double* plane, const double* rowc, int Ny, int NzG, int world, const int* bounds, int first_only,
-                            cudaStream_t st);
+cudaError_t launch_rebuild(double* plane, const double* rowc, int Ny, int NzG, int k0, int W, int first_only, cudaStream_t st);
+cudaError_t launch_assemble(const double* slab, double* plane, const double* rowc, int Ny, int NzG, int k0, int W, int first_only, cudaStream_t st);
 cudaError_t launch_dfma_peak(double* out, int blocks, int iters, cudaStream_t st);
 
 }  // namespace dfb

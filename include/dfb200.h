@@ -112,7 +112,8 @@ int dfb_dims(dfb_handle h, int* Ny, int* Nz);
  * 7 form of the z-sweep in use: 1 = recursive evaluation of the exponential window, 0 = direct Toeplitz sum,
  * 8 / 9 y-sweep tiles of the band-matrix kernels evaluated recursively / with dense band matrices,
  * 10 form of the y-sweep in use: 2 = run-recursive (every row group through the exponential window, the default), 1 = chunk-recursive
- *    band-matrix kernel, 0 = dense band matrices (DFB_Y_MODE forces a form), 11 tiles of the run-recursive kernel */
+ *    band-matrix kernel, 0 = dense band matrices (DFB_Y_MODE forces a form), 11 tiles of the run-recursive kernel, 12 transport of the config-4 hand-off: 2 = peer-to-peer copies (CUDA IPC + copy engines), 1 = NCCL
+ *    send/recv, 0 = no communicator */
 int dfb_info(dfb_handle h, int what, int field, int64_t* out64);
 /* host copies of the setup tables (for parity tests): which = 0..7 rows R11,R21,R22,R33,Us,Ts,rhos,Ms [Ny];
  * 8 yc row [Ny]; 9 dy row [Ny]; 10 Lt[3]; 11 coefficients of half-width `arg` [2*arg+1];
@@ -168,7 +169,12 @@ int dfb_host_unregister(void* ptr);
  *   per step:   dfb_filter(h, dt); dfb_gather_begin(h, dst); [dfb_filter(h, dt) of the next step ...]; dfb_gather_end(h);
  * dfb_gather_begin stages u', v', w' of the step just enqueued (the next dfb_filter may follow at once) and ships them -- 24 bytes per
  * cell; T', rho' are row-wise multiples of u' (df.cpp:470-485) and are rebuilt on the destination, bit for bit -- on a communication
- * stream; on the destination the slabs are assembled into row-major [Ny][Nz] planes.  dfb_gather_end blocks until that is done.
+ * stream, into row-major [Ny][Nz] planes on the destination.  dfb_gather_end blocks until that is done; the gathered plane stays valid
+ * until the next dfb_gather_begin.  Transport: NCCL sets the job up (communicator, exchange of the slab bounds and of CUDA IPC handles);
+ * the data itself goes peer to peer -- each sender's copy engine writes its slab straight into the destination plane's final layout
+ * over NVLink (strided 2-D copies), ordered by stream memory operations on flags: no SM is involved, so the hand-off of step t runs
+ * under the persistent sweep kernels of step t+1.  Where CUDA IPC is not available between the ranks (or with
+ * DFB_GATHER_TRANSPORT=nccl) the slabs go through ncclSend/ncclRecv and an assembly kernel instead.
  * A rank that only wants its own faces filled never gathers: it calls dfb_face_map + dfb_scatter_to_cells on its slab. */
 #define DFB_COMM_ID_BYTES 128
 int dfb_comm_unique_id(void* id128);
