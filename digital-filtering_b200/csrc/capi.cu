@@ -160,6 +160,8 @@ struct dfb_filter_s {
         if (copy) cudaStreamDestroy(copy);
         if (side) cudaStreamDestroy(side);
         if (stream) cudaStreamDestroy(stream);
+        cudaGetLastError();               // nothing above is checked (a peer that has already gone makes its IPC mapping fail to close):
+                                          // do not leave an error behind for the next call of this thread to trip over
     }
 };
 
@@ -1518,7 +1520,7 @@ void gather_p2p(dfb_filter_s& H, int dst_rank, int first_only) {
         struct Rec { cudaIpcMemHandle_t hd; int ok; int pad[3]; };
         Rec mine{};
         if (dst) mine.ok = cudaIpcGetMemHandle(&mine.hd, H.g_plane) == cudaSuccess ? 1 : 0;
-        Rec* dr = reinterpret_cast<Rec*>(H.dalloc<unsigned char>(sizeof(Rec) * (size_t)(world + 1)));
+        Rec* dr = reinterpret_cast<Rec*>(H.dalloc<unsigned char>(sizeof(Rec) * (size_t)(world + 1), false));
         CUDA_TRY(cudaMemcpyAsync(dr, &mine, sizeof(Rec), cudaMemcpyHostToDevice, H.comm_stream));
         NCCL_TRY(nccl().AllGather(dr, dr + 1, sizeof(Rec), ncclUint8, H.comm, H.comm_stream));
         std::vector<Rec> recs((size_t)world);
@@ -1589,9 +1591,11 @@ int dfb_comm_init(dfb_handle h, const void* id128, int rank, int world) {
             CUDA_TRY(cudaStreamCreateWithPriority(&h->asm_stream, cudaStreamNonBlocking, prio_hi));
             for (int r = 0; r < world; ++r) CUDA_TRY(cudaEventCreateWithFlags(&h->ev_slab[r], cudaEventDisableTiming));
         }
+        CUDA_TRY(cudaEventCreateWithFlags(&h->ev_gstaged, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&h->ev_gdone, cudaEventDisableTiming));
         // every rank learns every rank's slab: one all-gather of (k_begin, k_end, Ny, Nz_global)
         int mine[4] = {h->plan.k0, h->plan.k1, h->plan.Ny, h->plan.NzG};
-        int* d = h->dalloc<int>((size_t)4 * (world + 1));
+        int* d = h->dalloc<int>((size_t)4 * (world + 1), false);        // filled on comm_stream: no zeroing on the compute stream
         CUDA_TRY(cudaMemcpyAsync(d, mine, sizeof(mine), cudaMemcpyHostToDevice, h->comm_stream));
         NCCL_TRY(nccl().AllGather(d, d + 4, 4, ncclInt32, h->comm, h->comm_stream));
         std::vector<int> all((size_t)4 * world);
@@ -1622,7 +1626,7 @@ int dfb_comm_init(dfb_handle h, const void* id128, int rank, int world) {
             mine.ok = cudaIpcGetMemHandle(&mine.hd, h->flags) == cudaSuccess ? 1 : 0;
             if (mine.ok && cudaHostAlloc(reinterpret_cast<void**>(&h->seq_ring), 64 * sizeof(unsigned long long), cudaHostAllocPortable) != cudaSuccess) mine.ok = 0;
             cudaGetLastError();
-            Rec* dr = reinterpret_cast<Rec*>(h->dalloc<unsigned char>(sizeof(Rec) * (size_t)(world + 1)));
+            Rec* dr = reinterpret_cast<Rec*>(h->dalloc<unsigned char>(sizeof(Rec) * (size_t)(world + 1), false));
             CUDA_TRY(cudaMemcpyAsync(dr, &mine, sizeof(Rec), cudaMemcpyHostToDevice, h->comm_stream));
             NCCL_TRY(nccl().AllGather(dr, dr + 1, sizeof(Rec), ncclUint8, h->comm, h->comm_stream));
             std::vector<Rec> recs((size_t)world);
@@ -1637,7 +1641,7 @@ int dfb_comm_init(dfb_handle h, const void* id128, int rank, int world) {
                 h->peer_flags[r] = static_cast<unsigned long long*>(p);
             }
             // second round: did every rank manage to map every other rank?
-            int* dok = h->dalloc<int>((size_t)world + 1);
+            int* dok = h->dalloc<int>((size_t)world + 1, false);
             CUDA_TRY(cudaMemcpyAsync(dok, &ok, sizeof(int), cudaMemcpyHostToDevice, h->comm_stream));
             NCCL_TRY(nccl().AllGather(dok, dok + 1, 1, ncclInt32, h->comm, h->comm_stream));
             std::vector<int> oks((size_t)world);
@@ -1685,7 +1689,7 @@ int dfb_gather_begin(dfb_handle h, int dst_rank) {
         const bool dst = h->comm_rank == dst_rank;
         if (dst && (!h->g_plane || h->g_dst != dst_rank)) {
             if (!h->g_plane) {
-                h->g_plane = h->dalloc<double>((size_t)5 * Ny * NzG);
+                h->g_plane = h->dalloc<double>((size_t)5 * Ny * NzG, false);
                 h->g_recv = h->dalloc<double>((size_t)3 * Ny * NzG, false);
                 h->g_recv_off.assign(world + 1, 0);
                 for (int r = 0; r < world; ++r)

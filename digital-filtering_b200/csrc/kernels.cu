@@ -1275,6 +1275,7 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, 
 // =================================================================================================
 cudaError_t launch_noise(const NoiseParams& P, const PlaneDev& D, cudaStream_t st) {
     if (P.n_arrays == 0) return cudaSuccess;
+    cudaGetLastError();        // the status returned below is this launch's, not a leftover of an unrelated earlier call
     int max_seg = 0;
     for (int a = 0; a < P.n_arrays; ++a) max_seg = P.a[a].n_seg > max_seg ? P.a[a].n_seg : max_seg;
     dim3 grid((unsigned)P.chunks, (unsigned)max_seg, (unsigned)(P.n_arrays * D.P));

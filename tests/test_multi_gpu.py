@@ -37,7 +37,7 @@ def test_gather_through_the_c_abi(dfb, world):
     subprocess.run(["/usr/bin/gcc", "-std=c11", "-Wall", "-D_POSIX_C_SOURCE=200809L", "-I" + os.path.join(ROOT, "include"),
                     os.path.join(ROOT, "tests", "comm_c_test.c"), "-L" + LIBDIR, "-ldfb200", "-Wl,-rpath," + LIBDIR, "-o", exe],
                    check=True, capture_output=True)
-    r = subprocess.run([exe, str(world)], capture_output=True, text=True, timeout=600)
+    r = subprocess.run([exe, str(world)], capture_output=True, text=True, timeout=180)
     assert r.returncode == 0, (r.stdout, r.stderr[-2000:])
     tok = [ln for ln in r.stdout.splitlines() if ln.startswith("OK ")][-1].split()      # (NCCL prints its version banner on stdout)
     assert tok[0] == "OK" and int(tok[1]) == world and int(tok[4]) > 0
