@@ -199,6 +199,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "bra W_%=;\n\t"
         "D_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// the same, yielding the issue slot between polls: for waits that are expected to be long (a whole tile being staged) beside warps
+// that have work to do
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (;;) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(200);
+    }
+}
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
@@ -641,7 +654,7 @@ __global__ void __launch_bounds__(32 * (YR_CONSUMERS + 1), 1) ysweep_run_kernel(
     int i = 0;
     for (int tix = blockIdx.x; tix < n_all; tix += gridDim.x, ++i) {
         const int s = i % nbuf;
-        mbar_wait(&ctl.full[s], (i / nbuf) & 1);
+        mbar_wait_backoff(&ctl.full[s], (i / nbuf) & 1);
         const YRTile& t = ctl.tile[s];
         const int pl = ctl.plane[s];
         const FieldDev& F = P.D.f[t.field];
@@ -666,24 +679,28 @@ __global__ void __launch_bounds__(32 * (YR_CONSUMERS + 1), 1) ysweep_run_kernel(
                 if (i0 + 3 <= N) { f3 = col[(c - i0 - 3) * YR_C]; b3 = col[(ct + i0 + 3) * YR_C]; }
                 const double* pf = col + (size_t)(c - i0 + 4) * YR_C;   // term 4(m-1) of chain 0 on the F side
                 const double* pb = col + (size_t)(ct + i0 - 4) * YR_C;
-                // software pipeline: the eight samples of the next step are requested before the eight FMAs of this one
-                double nf0 = 0.0, nf1 = 0.0, nf2 = 0.0, nf3 = 0.0, nb0 = 0.0, nb1 = 0.0, nb2 = 0.0, nb3 = 0.0;
-                if (m > 0) {
-                    nf0 = pf[0]; nf1 = pf[-YR_C]; nf2 = pf[-2 * YR_C]; nf3 = pf[-3 * YR_C];
-                    nb0 = pb[0]; nb1 = pb[YR_C]; nb2 = pb[2 * YR_C]; nb3 = pb[3 * YR_C];
-                }
-#pragma unroll 2
-                for (--m; m >= 0; --m) {
-                    const double xf0 = nf0, xf1 = nf1, xf2 = nf2, xf3 = nf3, xb0 = nb0, xb1 = nb1, xb2 = nb2, xb3 = nb3;
+                // Software pipeline with two register sets (no copies): the eight samples of step m-1 are requested before the eight FMAs
+                // of step m.  Steps come in pairs; an odd step count is settled first.
+                auto load8 = [&](double* x) {
+                    x[0] = pf[0]; x[1] = pf[-YR_C]; x[2] = pf[-2 * YR_C]; x[3] = pf[-3 * YR_C];
+                    x[4] = pb[0]; x[5] = pb[YR_C]; x[6] = pb[2 * YR_C]; x[7] = pb[3 * YR_C];
                     pf += 4 * YR_C; pb -= 4 * YR_C;
-                    if (m > 0) {
-                        nf0 = pf[0]; nf1 = pf[-YR_C]; nf2 = pf[-2 * YR_C]; nf3 = pf[-3 * YR_C];
-                        nb0 = pb[0]; nb1 = pb[YR_C]; nb2 = pb[2 * YR_C]; nb3 = pb[3 * YR_C];
+                };
+                auto fma8 = [&](const double* x) {
+                    f0 = __fma_rn(a4, f0, x[0]); b0 = __fma_rn(a4, b0, x[4]);
+                    f1 = __fma_rn(a4, f1, x[1]); b1 = __fma_rn(a4, b1, x[5]);
+                    f2 = __fma_rn(a4, f2, x[2]); b2 = __fma_rn(a4, b2, x[6]);
+                    f3 = __fma_rn(a4, f3, x[3]); b3 = __fma_rn(a4, b3, x[7]);
+                };
+                double xa[8], xb[8];
+                if (m & 1) { load8(xa); fma8(xa); --m; }                 // m steps remain, now even
+                if (m > 0) {
+                    load8(xa);
+                    for (; m > 2; m -= 2) {
+                        load8(xb); fma8(xa);
+                        load8(xa); fma8(xb);
                     }
-                    f0 = __fma_rn(a4, f0, xf0); b0 = __fma_rn(a4, b0, xb0);
-                    f1 = __fma_rn(a4, f1, xf1); b1 = __fma_rn(a4, b1, xb1);
-                    f2 = __fma_rn(a4, f2, xf2); b2 = __fma_rn(a4, b2, xb2);
-                    f3 = __fma_rn(a4, f3, xf3); b3 = __fma_rn(a4, b3, xb3);
+                    load8(xb); fma8(xa); fma8(xb);
                 }
             }
             double Fc = __fma_rn(a, __fma_rn(a, __fma_rn(a, f3, f2), f1), f0);
