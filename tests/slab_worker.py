@@ -45,6 +45,8 @@ def main():
             for w in range(5):
                 ok &= bool(np.array_equal(got[s][w], ref[w]))
         assert not got[0][3].any() and got[1][3].any()
+        want = {"p2p": 2, "nccl": 1}.get(os.environ.get("DFB_GATHER_TRANSPORT", "p2p"), 2)
+        assert sf.filt.info(12) == want, (sf.filt.info(12), want)
         wire = sf.filt.gather_wire_bytes()
         assert wire == 24 * plane["Ny"] * (plane["Nz"] - (sf.k1 - sf.k0)), wire        # u', v', w' of the other ranks' slabs
         whole.close()

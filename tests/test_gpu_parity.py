@@ -450,7 +450,12 @@ def test_explicit_odd_and_mixed_half_widths(dfb, O, W):
     assert _run_explicit(dfb, O, plane, seed=12, dts=[3e-7])     # row-uniform -> tuned kernels, scalar z staging (odd N)
 
 
-def test_large_half_widths_beyond_128(dfb, O, W):
+@pytest.mark.parametrize("ymode", [None, "2"], ids=["y-default", "y-run-forced"])
+def test_large_half_widths_beyond_128(dfb, O, W, monkeypatch, ymode):
+    """half-widths up to 300: the windows are too tall for two buffers of the run-recursive y-sweep, so by default the band-matrix
+    kernels take the plane; forced (DFB_Y_MODE=2) the run form runs with ONE window buffer per CTA -- both against the oracle."""
+    if ymode is not None:
+        monkeypatch.setenv("DFB_Y_MODE", ymode)
     Ny, Nz = 24, 700
     Nyr = [np.full(Ny, 200), np.full(Ny, 96), np.linspace(20, 260, Ny).astype(int) // 2 * 2]
     Nzr = [np.full(Ny, 300), np.full(Ny, 2), np.full(Ny, 130)]

@@ -43,10 +43,13 @@ def test_gather_through_the_c_abi(dfb, world):
     assert tok[0] == "OK" and int(tok[1]) == world and int(tok[4]) > 0
 
 
+@pytest.mark.parametrize("transport", ["p2p", "nccl"])
 @pytest.mark.parametrize("world", [2])
-def test_slab_filter_python_caller(dfb, world):
+def test_slab_filter_python_caller(dfb, world, transport, monkeypatch):
+    """both transports of the hand-off: peer-to-peer copies (CUDA IPC + copy engines, the default) and ncclSend/ncclRecv + assembly"""
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
+    monkeypatch.setenv("DFB_GATHER_TRANSPORT", transport)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
                         "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "slab_worker.py")],
                        capture_output=True, text=True, timeout=900)
