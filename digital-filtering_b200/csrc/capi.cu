@@ -663,6 +663,21 @@ void build_device(dfb_filter_s& H) {
             for (const Item& it : by_cost(2, -1)) units.push_back(make_unit(it, 2));
             units.push_back(ZUnit{});                                // the last single item is fetched as 8 ints: nothing to pad, but keep the array non-empty-safe
             Z.units = H.upload(units);
+            Z.unit_par = nullptr;
+            if (Z.zmode == 1) {
+                // one record per (row, field): the half-width's parameter line + the row's epilogue constants
+                std::vector<double> par((size_t)Ny * 3 * (16 + ROWC), 0.0);
+                for (int j = 0; j < Ny; ++j)
+                    for (int f = 0; f < 3; ++f) {
+                        const int N = P.f[f].N_z_row[j];
+                        const int d = ((-N) % ZKc + ZKc) % ZKc;
+                        const int clen = round_up((1 + (2 * N + d + ZKc - 1) / ZKc + 1) * ZKc, 16) + 16;
+                        double* q = par.data() + ((size_t)j * 3 + f) * (16 + ROWC);
+                        std::copy(pvals.begin() + pptr[N] + clen - 16, pvals.begin() + pptr[N] + clen, q);
+                        std::copy(rowc.begin() + (size_t)j * ROWC, rowc.begin() + (size_t)(j + 1) * ROWC, q + 16);
+                    }
+                Z.unit_par = H.upload(par);
+            }
             Z.n_uv = (int)items.size();
             Z.n_items = 2 * (int)items.size();
             Z.counter = H.dalloc<int>(2);        // one work counter per buffer set: y(s+1) resets its own while z(s) still pulls from the other
@@ -1456,8 +1471,8 @@ int dfb_debug_zprof(dfb_handle h, unsigned long long* out8) {
     return guarded([&] {
         CUDA_TRY(cudaStreamSynchronize(h->stream));
         if (!h->zp[0].prof) throw Error{DFB_ERR_STATE, "no profile buffer"};
-        CUDA_TRY(cudaMemcpy(out8, h->zp[0].prof, 64, cudaMemcpyDeviceToHost));
-        CUDA_TRY(cudaMemset(h->zp[0].prof, 0, 64));
+        CUDA_TRY(cudaMemcpy(out8, h->zp[0].prof, 128, cudaMemcpyDeviceToHost));      // 16 counters
+        CUDA_TRY(cudaMemset(h->zp[0].prof, 0, 128));
     });
 }
 

@@ -168,6 +168,8 @@ struct ZParams {
     int* counter;                // work counter, zeroed by the y-sweep that precedes this launch
     const double* coef_pad;      // padded coefficient vectors B_N[m] = b_N[m - 16 - d(N)], zero elsewhere, + one 128-byte header line each
     const long long* coef_pad_ptr;   // [Nmax+1] offsets (doubles, 16-byte aligned) into coef_pad
+    const double* unit_par;      // recursive form: per (row, field) the parameter line (16 doubles) followed by the row's ROWC epilogue
+                                 // constants: what a unit stages after its window, as ONE record; nullptr in the direct form
     double* stats;               // N2 running sums [P][6][Ny*W] (u'^2, v'^2, w'^2, T'^2, rho'^2, u'v') accumulated by this launch, or nullptr
     int zk;                      // outputs per lane: 16 (128-byte lines) or 8 (64-byte lines); an item is 32*zk columns
     int box_lines;               // lines per staged window (box height of the tensor maps)

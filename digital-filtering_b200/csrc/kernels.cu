@@ -798,8 +798,14 @@ __device__ __forceinline__ void z_issue_unit(const ZParams& P, const ZMaps& maps
     unsigned char* b = reinterpret_cast<unsigned char*>(buf);
     mbar_expect_tx(bar, (uint32_t)P.box_bytes + cbytes + (uint32_t)(ROWC * sizeof(double)) + (fo ? strip_bytes : 0u));
     tma_load_3d(b, &maps.m[f], 0, desc[4], plane * P.D.Ny + j, bar);
-    tma_load_1d(b + P.box_bytes, P.coef_pad + (size_t)desc[6] * 16, cbytes, bar);
-    tma_load_1d(b + P.rc_off, P.D.rowc + (size_t)j * ROWC, ROWC * sizeof(double), bar);
+    if (P.unit_par) {
+        // recursive form: the row's parameter line and its epilogue constants sit side by side in one record per (row, field):
+        // one bulk copy instead of two (issuing a TMA operation costs the lone issuing lane ~200 cycles)
+        tma_load_1d(b + P.box_bytes, P.unit_par + ((size_t)j * 3 + f) * (16 + ROWC), (16 + ROWC) * sizeof(double), bar);
+    } else {
+        tma_load_1d(b + P.box_bytes, P.coef_pad + (size_t)desc[6] * 16, cbytes, bar);
+        tma_load_1d(b + P.rc_off, P.D.rowc + (size_t)j * ROWC, ROWC * sizeof(double), bar);
+    }
     if (fo) tma_load_1d(b + P.fo_off, P.D.f[f].filt_old + (size_t)plane * P.D.ps_cells + (size_t)j * P.D.W + c0, strip_bytes, bar);
 }
 
@@ -848,7 +854,9 @@ __global__ void __maxnreg__(MODE == 1 ? Z_REC_MAXNREG : 168) zsweep_epilogue_ker
     int itemB = __shfl_sync(0xffffffffu, claim, 0);
     if (itemB < n_total && lane < 16) descs[16 + lane] = fetch_item(itemB);
     __syncwarp();
-    if (lane == 0) z_issue_unit(P, maps, descs, itemA % nP, wbase, &bars[0]);
+    int plA = itemA % nP, plB = itemB % nP;                 // plane of a batch (0 for a single plane), kept per item: no division per unit
+    int unA = item_units(itemA);
+    if (lane == 0) z_issue_unit(P, maps, descs, plA, wbase, &bars[0]);
 
     // Pipeline per unit n (buffer n & 1, barrier phase (n >> 1) & 1); an item is the three consecutive units u, v, w:
     //   top:    stage unit n+1 (the v unit of this pair, or the first unit of the next item, whose descriptors are already in shared
@@ -856,27 +864,31 @@ __global__ void __maxnreg__(MODE == 1 ? Z_REC_MAXNREG : 168) zsweep_epilogue_ker
     //   middle: tap loop of unit n
     //   bottom: epilogue of unit n; at an item's last unit fetch the descriptors of the newly claimed item into the slot just vacated
     int slot = 0, phase = 0;
+    long long pa_wait = 0, pa_taps = 0, pa_epi = 0, pa_unit = 0, pa_top = 0, pa_stage = 0, pa_n = 0;   // DFB_DEBUG_Z & 16: per-warp phase cycles,
+                                                                                                       // flushed once at the warp's exit
     for (int n = 0;; ++n) {
+        const long long ttop = (P.debug & 16) ? clock64() : 0;
         const int* dcur = descs + slot * 16 + phase * 8;
-        const bool last_phase = phase == item_units(itemA) - 1;
+        const bool last_phase = phase == unA - 1;
         const bool have_next = !last_phase || itemB < n_total;
         if (have_next && lane == 0) {
             unsigned char* nb = wbase + (size_t)((n + 1) & 1) * P.unit_bytes;
             const int* dnext = last_phase ? descs + (slot ^ 1) * 16 : dcur + 8;
-            z_issue_unit(P, maps, dnext, (last_phase ? itemB : itemA) % nP, nb, &bars[(n + 1) & 1]);
+            z_issue_unit(P, maps, dnext, last_phase ? plB : plA, nb, &bars[(n + 1) & 1]);
         }
+        if (P.debug & 16) pa_stage += clock64() - ttop;                                           // staging the next unit (lane 0)
         if (phase == 0 && itemB < n_total && lane == 0) claim = atomicAdd(P.counter, 1);        // the item after the next
 
         const int j = dcur[0], c0 = dcur[1], f = dcur[2];
         const int nchunk = __shfl_sync(0xffffffffu, dcur[3], 0);
         const int k0 = c0 + lane * ZK;
         const bool active = k0 < D.W;
-        const size_t pbase = (size_t)(itemA % nP) * D.ps_cells;                // this plane's share of the dense output arrays
+        const size_t pbase = (size_t)plA * D.ps_cells;                        // this plane's share of the dense output arrays
         const size_t base = pbase + (size_t)j * D.W + k0;
         const size_t sbase = pbase + (size_t)j * D.W + c0;                    // first cell of the warp's strip
         // whole strip inside the plane and 16-byte aligned: piece-major epilogue (coalesced global access); its filt_old strip was
         // staged with the window
-        const bool coalesced = z_strip_coalesced(P, j, c0, itemA % nP);
+        const bool coalesced = z_strip_coalesced(P, j, c0, plA);
         const FieldDev& F = D.f[f];
         const bool blend = !P.S.first_step;
         const long long tunit = (P.debug & 16) ? clock64() : 0;
@@ -1056,7 +1068,7 @@ __global__ void __maxnreg__(MODE == 1 ? Z_REC_MAXNREG : 168) zsweep_epilogue_ker
             const double rc_own = rc[f == 0 ? 0 : (f == 1 ? 2 : 3)];
             const double rc0 = rc[0], rc1 = rc[1], rc4 = rc[4], rc5 = rc[5], rc6 = rc[6];
             const double sa = P.S.sa[f], sb = P.S.sb[f];
-            double* stats = (STATS && blend) ? P.stats + (size_t)(itemA % nP) * 6 * D.ps_cells + ((size_t)j * D.W) : nullptr;
+            double* stats = (STATS && blend) ? P.stats + (size_t)plA * 6 * D.ps_cells + ((size_t)j * D.W) : nullptr;
             if (coalesced) {
                 // One transpose per unit: lane l owns line l (its ZK cells) of a 32-line tile; global memory wants 16-byte piece
                 // p = lane + 32 m of the strip.  The tap loop's results go through the (swizzled, conflict-free both ways) tile once;
@@ -1149,17 +1161,20 @@ __global__ void __maxnreg__(MODE == 1 ? Z_REC_MAXNREG : 168) zsweep_epilogue_ker
             }
             __syncwarp();                // tile / staged-strip reads are done before the buffer is refilled by the next-but-one unit
         }
-        if ((P.debug & 16) && lane == 0) {
+        if (P.debug & 16) {
             const long long t3 = clock64();
-            atomicAdd(P.prof + 0, (unsigned long long)(t1 - t0));     // waiting for the staged unit
-            atomicAdd(P.prof + 1, (unsigned long long)(t2 - t1));     // tap loop
-            atomicAdd(P.prof + 2, (unsigned long long)(t3 - t2));     // epilogue
-            atomicAdd(P.prof + 3, (unsigned long long)(t3 - tunit));  // whole unit
-            atomicAdd(P.prof + 4, 1ull);
+            pa_wait += t1 - t0; pa_taps += t2 - t1; pa_epi += t3 - t2; pa_unit += t3 - tunit; pa_top += tunit - ttop; pa_n += 1;
         }
         if (!have_next) {
             if (lane == 0) tl_stamp(P.tl, 1);
             if ((P.debug & 16) && lane == 0) {
+                atomicAdd(P.prof + 0, (unsigned long long)pa_wait);       // waiting for the staged unit
+                atomicAdd(P.prof + 1, (unsigned long long)pa_taps);       // tap loop
+                atomicAdd(P.prof + 2, (unsigned long long)pa_epi);        // epilogue
+                atomicAdd(P.prof + 3, (unsigned long long)pa_unit);       // whole unit
+                atomicAdd(P.prof + 4, (unsigned long long)pa_n);
+                atomicAdd(P.prof + 8, (unsigned long long)pa_stage);      // staging the next unit (lane 0)
+                atomicAdd(P.prof + 9, (unsigned long long)pa_top);        // top of the loop: staging + claim + addressing
                 const unsigned long long life = (unsigned long long)(clock64() - tstart);
                 atomicAdd(P.prof + 5, life);
                 atomicMax(P.prof + 6, life);
@@ -1172,6 +1187,7 @@ __global__ void __maxnreg__(MODE == 1 ? Z_REC_MAXNREG : 168) zsweep_epilogue_ker
             if (itemC < n_total && lane < 16) descs[slot * 16 + lane] = dreg;
             __syncwarp();
             itemA = itemB; itemB = itemC; slot ^= 1; phase = 0;
+            plA = plB; plB = itemC % nP; unA = item_units(itemA);
         } else {
             ++phase;
         }
