@@ -871,13 +871,14 @@ __global__ void __maxnreg__(MODE == 1 ? Z_REC_MAXNREG : 168) zsweep_epilogue_ker
         const int* dcur = descs + slot * 16 + phase * 8;
         const bool last_phase = phase == unA - 1;
         const bool have_next = !last_phase || itemB < n_total;
+        if (phase == 0 && itemB < n_total && lane == 0) claim = atomicAdd(P.counter, 1);        // the item after the next: requested first,
+                                                                                                // its round trip hides behind everything below
         if (have_next && lane == 0) {
             unsigned char* nb = wbase + (size_t)((n + 1) & 1) * P.unit_bytes;
             const int* dnext = last_phase ? descs + (slot ^ 1) * 16 : dcur + 8;
             z_issue_unit(P, maps, dnext, last_phase ? plB : plA, nb, &bars[(n + 1) & 1]);
         }
         if (P.debug & 16) pa_stage += clock64() - ttop;                                           // staging the next unit (lane 0)
-        if (phase == 0 && itemB < n_total && lane == 0) claim = atomicAdd(P.counter, 1);        // the item after the next
 
         const int j = dcur[0], c0 = dcur[1], f = dcur[2];
         const int nchunk = __shfl_sync(0xffffffffu, dcur[3], 0);
@@ -1094,10 +1095,8 @@ __global__ void __maxnreg__(MODE == 1 ? Z_REC_MAXNREG : 168) zsweep_epilogue_ker
                     *gs = make_double2(__dadd_rn(cur.x, __dmul_rn(x.x, y.x)), __dadd_rn(cur.y, __dmul_rn(x.y, y.y)));
                 };
                 const int npieces = min(32 * ZK, D.W - c0) >> 1;                            // 16-byte pieces of the strip inside the slab
-#pragma unroll
-                for (int m = 0; m < ZK / 2; ++m) {
+                auto piece = [&](int m) {
                     const int pc = lane + 32 * m, r = pc / PPL;
-                    if (pc >= npieces) break;
                     double2 z = *reinterpret_cast<const double2*>(cbuf + r * LB + ((((pc % PPL) ^ swz(r))) << 4));
                     if (blend) {                                                                 // correlate_fields, df.cpp:415
                         const double2 fo = fo_t[pc];
@@ -1121,6 +1120,14 @@ __global__ void __maxnreg__(MODE == 1 ? Z_REC_MAXNREG : 168) zsweep_epilogue_ker
                         __stcs(g_r + pc, rv);
                         if (STATS && stats) { add2(3, pc, Tv, Tv); add2(4, pc, rv, rv); }
                     }
+                };
+                if (npieces == 16 * ZK) {                    // whole strip (the common case): no guard, the eight pieces' loads overlap
+#pragma unroll
+                    for (int m = 0; m < ZK / 2; ++m) piece(m);
+                } else {
+#pragma unroll
+                    for (int m = 0; m < ZK / 2; ++m)
+                        if (lane + 32 * m < npieces) piece(m);
                 }
             } else {
                 // partial / unaligned strip: every lane walks its own cells in global memory; u's strip waits in the line buffer in
