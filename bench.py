@@ -532,9 +532,10 @@ def run_b200(args, plane):
     hbm_src = "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"
     alg_bytes = 88 * cells                                    # 5 outputs + filt_old r/w x3
     zmode = "recursive" if df.info(7) == 1 else "direct"
-    y_form = {2: "run-recursive", 1: "chunk-recursive band matrices", 0: "dense band matrices"}[int(df.info(10))]
+    y_form = {3: "run-recursive on the row blocks where it pays + dense band matrices on the rest", 2: "run-recursive",
+              1: "chunk-recursive band matrices", 0: "dense band matrices"}[int(df.info(10))]
     y_bytes = 3 * 16 * cells                                  # y-sweep: r_ys read once, r_zs interior written once, per field
-    yname = "ysweep_run_kernel" if df.info(10) == 2 else "ysweep_tma_kernel"
+    yname = "ysweep_run_kernel" if df.info(10) >= 2 else "ysweep_tma_kernel"
     kern = {
         # y-sweep.  Run-recursive form: every row group through the exponential window, ~5x fewer flops than the reference's
         # 2*(2N_y+1) per cell -> its roof is the memory system; equivalent_tflops = reference-formulation flops / time, for comparison.

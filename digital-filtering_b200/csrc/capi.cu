@@ -265,6 +265,130 @@ void build_device(dfb_filter_s& H) {
         std::vector<YGroup> groups;
         std::vector<YTile> tiles;
         std::vector<double> cmat;
+        // ---- which rows go through the run-recursive form (ysweep_run_kernel), which through the band matrices ----
+        // The run form evaluates a group of R <= 8 rows of ONE half-width N with 2(N+1) + 4R multiply-adds per column where the direct sum
+        // spends R(2N+1): it pays in runs of equal N, not where N changes every row or two (a lone row costs its direct sum and
+        // its window has to be staged whole).  Decided per block of 32 rows: run form where it executes less than half of the
+        // direct sum's multiply-adds (and two of the block's windows fit in shared memory); the other rows keep the band matrices.
+        // DFB_Y_MODE=2 forces the run form wherever a window fits at all, 0 / 1 force the band-matrix kernels (dense / chunk-recursive).
+        const int ymode_env = std::getenv("DFB_Y_MODE") ? std::atoi(std::getenv("DFB_Y_MODE")) : -1;
+        cudaDeviceProp yprop;
+        CUDA_TRY(cudaGetDeviceProperties(&yprop, H.device));
+        std::vector<char> run_row[3];
+        std::vector<YRGroup> rg;
+        std::vector<YRTile> rt;
+        int r_wrows = 0, r_nbuf = 2;
+        {
+            constexpr int CB = 32;                                   // classification block
+            for (int f = 0; f < 3; ++f) {
+                const std::vector<int>& Nr = P.f[f].N_y_row;
+                run_row[f].assign(Ny, 0);
+                if (ymode_env == 0 || ymode_env == 1) continue;
+                for (int jb = 0; jb < Ny; jb += CB) {
+                    const int je = std::min(Ny, jb + CB);
+                    double c_run = 0, c_dense = 0;
+                    for (int j = jb; j < je;) {
+                        int R = 1;
+                        while (j + R < je && R < YJ && Nr[j + R] == Nr[j]) ++R;
+                        c_run += 2.0 * (Nr[j] + 1) + 4.0 * R;
+                        for (int t = 0; t < R; ++t) c_dense += 2.0 * Nr[j + t] + 1.0;
+                        j += R;
+                    }
+                    // ... and only where a 128-row block of such rows fits twice into shared memory (N up to ~150): taller windows force
+                    // short blocks, which re-read their windows many times over (measured on the reference's default plane, N_y up to
+                    // 212: 32-row blocks with 400-row windows made the y-sweep slower than the band matrices alone)
+                    int Nm = 0;
+                    for (int j = jb; j < je; ++j) Nm = std::max(Nm, Nr[j]);
+                    const bool roomy = ysweep_run_smem(round_up(128 + 2 * Nm, YR_BOX), 2) <= (size_t)yprop.sharedMemPerBlockOptin;
+                    if (ymode_env == 2 || (c_run < 0.5 * c_dense && roomy)) std::fill(run_row[f].begin() + jb, run_row[f].begin() + je, 1);
+                }
+            }
+            // run plan over the run rows: maximal contiguous ranges chopped into blocks of RB rows; a block x 32 columns = one tile
+            auto build = [&](int RB) {
+                rg.clear(); rt.clear();
+                int wmax = 0;
+                for (int f = 0; f < 3; ++f) {
+                    const FieldPlan& FP = P.f[f];
+                    for (int ja = 0; ja < Ny;) {
+                        if (!run_row[f][ja]) { ++ja; continue; }
+                        int jz = ja;
+                        while (jz < Ny && run_row[f][jz]) ++jz;                       // run range [ja, jz)
+                        for (int jb = ja; jb < jz; jb += RB) {
+                            const int je = std::min(jz, jb + RB);
+                            std::vector<YRGroup> blk;
+                            for (int j0 = jb; j0 < je;) {
+                                const int N = FP.N_y_row[j0];
+                                int R = 1;
+                                while (j0 + R < je && R < YJ && FP.N_y_row[j0 + R] == N) ++R;
+                                YRGroup g{};
+                                g.j0 = j0; g.nrows = R; g.N = N;
+                                if (N >= 1) {
+                                    const long double a = (long double)std::exp(-2.0 * 3.14159265358979323846 * 1.0 / N);
+                                    g.a = (double)a;
+                                    g.a4 = (double)(a * a * a * a);
+                                    g.naN1 = -(double)std::pow(a, (long double)(N + 1));
+                                }
+                                g.inv_s = *P.coef.centre(N);
+                                blk.push_back(g);
+                                j0 += R;
+                            }
+                            std::stable_sort(blk.begin(), blk.end(), [](const YRGroup& x, const YRGroup& y) { return 2 * x.N + 4 * x.nrows > 2 * y.N + 4 * y.nrows; });
+                            YRTile t{};
+                            t.field = f; t.g0 = (int)rg.size(); t.ngroups = (int)blk.size();
+                            int lo = 1 << 30, hi = -1;
+                            for (const YRGroup& g : blk) {
+                                lo = std::min(lo, g.j0 + FP.Ny_max - g.N);
+                                hi = std::max(hi, g.j0 + g.nrows - 1 + FP.Ny_max + g.N);
+                            }
+                            t.wlo = lo; t.wrows = hi - lo + 1;
+                            wmax = std::max(wmax, round_up(t.wrows, YR_BOX));
+                            rg.insert(rg.end(), blk.begin(), blk.end());
+                            for (int c0 = 0; c0 < D.f[f].We; c0 += YR_C) { t.col0 = c0; rt.push_back(t); }
+                        }
+                        ja = jz;
+                    }
+                }
+                return wmax;
+            };
+            const size_t smem_cap = (size_t)yprop.sharedMemPerBlockOptin;
+            bool fits = false;
+            for (int pass = 0; pass < 2 && !fits; ++pass) {
+                for (int RB : {128, 64, 32}) {
+                    r_wrows = build(RB); r_nbuf = 2;
+                    if (rt.empty() || ysweep_run_smem(r_wrows, 2) <= smem_cap) { fits = true; break; }
+                }
+                if (fits) break;
+                if (ymode_env == 2) {
+                    // forced: one window buffer per CTA before giving a block up
+                    for (int RB : {128, 64, 32}) {
+                        r_wrows = build(RB); r_nbuf = 1;
+                        if (ysweep_run_smem(r_wrows, 1) <= smem_cap) { fits = true; break; }
+                    }
+                    if (fits) break;
+                }
+                // blocks whose own window is too tall go back to the band matrices, then one more try
+                const int nb = ymode_env == 2 ? 1 : 2;
+                for (int f = 0; f < 3; ++f)
+                    for (int jb = 0; jb < Ny; jb += CB) {
+                        if (!run_row[f][jb]) continue;
+                        const int je = std::min(Ny, jb + CB);
+                        int Nm = 0;
+                        for (int j = jb; j < je; ++j) Nm = std::max(Nm, P.f[f].N_y_row[j]);
+                        if (ysweep_run_smem(round_up(CB + 2 * Nm, YR_BOX), nb) > smem_cap) std::fill(run_row[f].begin() + jb, run_row[f].begin() + je, 0);
+                    }
+            }
+            if (!fits) { for (int f = 0; f < 3; ++f) run_row[f].assign(Ny, 0); rg.clear(); rt.clear(); }
+        }
+        bool any_run = !rt.empty(), any_band = false;
+        for (int f = 0; f < 3; ++f) for (int j = 0; j < Ny; ++j) any_band = any_band || !run_row[f][j];
+        // Both forms on one plane = two y-sweep launches per step; that only pays when the run-recursive part has enough tiles to
+        // fill the machine a few times over (measured on the reference's default plane: alone 49.6 us per step against 42.5 with the
+        // band matrices only; as a batch of 8 planes 20.8 us per plane-step against 23.8)
+        if (any_run && any_band && ymode_env < 0 && (long long)rt.size() * NP < 4ll * yprop.multiProcessorCount) {
+            for (int f = 0; f < 3; ++f) run_row[f].assign(Ny, 0);
+            rg.clear(); rt.clear();
+            any_run = false;
+        }
         // Row groups.  The reference's coefficients are b_i = a^|i| / s (df.cpp:168-177): a group whose rows all have the same
         // half-width N >= 16 is evaluated recursively (ysweep_rec_kernel: ~1 FMA per input row and column instead of 8); the
         // others keep the dense band matrix.  N_y changes every few rows on boundary-layer grids, so groups follow the runs of
@@ -310,8 +434,8 @@ void build_device(dfb_filter_s& H) {
                     }
                 }
             }
-            yrec_on = hybrid < 0.6 * dense;
-            if (const char* ym = std::getenv("DFB_Y_MODE")) yrec_on = std::atoi(ym) != 0;
+            yrec_on = !any_run && hybrid < 0.6 * dense;               // (rows the run form took are the ones this would have paid on)
+            if (ymode_env >= 0) yrec_on = ymode_env == 1;
         }
         std::vector<char> yrec_need(P.coef.Nmax + 1, 0);
         std::vector<double> ygc(16, 0.0);     // recursive groups: 8 low-bulk + 8 high-bulk factors each; entry 0 = zeros (mixed groups)
@@ -321,17 +445,22 @@ void build_device(dfb_filter_s& H) {
         int ytk = Y_TK;
         if (!yrec_on) {
             long long est = 0;
-            for (int f = 0; f < 3; ++f) est += (long long)((D.f[f].We + Y_TK - 1) / Y_TK) * (((Ny + YJ - 1) / YJ + Y_G - 1) / Y_G);
+            for (int f = 0; f < 3; ++f) {
+                const int nband = (int)std::count(run_row[f].begin(), run_row[f].end(), 0);
+                est += (long long)((D.f[f].We + Y_TK - 1) / Y_TK) * (((nband + YJ - 1) / YJ + Y_G - 1) / Y_G);
+            }
             int nymax = 0;
             for (int f = 0; f < 3; ++f) nymax = std::max(nymax, P.f[f].Ny_max);
-            if (est < 2 * 148 && nymax >= 64) ytk = 64;      // few, very long tiles (measured: 512x512 N <= 32 prefers 128)
+            if (est * NP < 2 * 148 && nymax >= 64) ytk = 64;      // few, very long tiles (measured: 512x512 N <= 32 prefers 128); a batch has NP times as many
             if (const char* e = std::getenv("DFB_Y_TK")) ytk = std::atoi(e) == 64 ? 64 : Y_TK;
         }
         for (int f = 0; f < 3; ++f) {
             const FieldPlan& FP = P.f[f];
             std::vector<YGroup> gk[2];        // [0] dense (mixed half-widths or small N), [1] recursive, each in row order
-            auto run_len = [&](int j) { int r = 1; while (j + r < Ny && FP.N_y_row[j + r] == FP.N_y_row[j]) ++r; return r; };
+            // (rows of the run-recursive form are skipped; a run of equal N ends where such rows begin)
+            auto run_len = [&](int j) { int r = 1; while (j + r < Ny && !run_row[f][j + r] && FP.N_y_row[j + r] == FP.N_y_row[j]) ++r; return r; };
             for (int j0 = 0; j0 < Ny;) {
+                if (run_row[f][j0]) { ++j0; continue; }
                 YGroup g{};
                 int nr;
                 bool uniform = false;
@@ -340,7 +469,7 @@ void build_device(dfb_filter_s& H) {
                 else {
                     // mixed group: up to YJ rows, but stop in front of a run long enough to be worth its own recursive groups
                     nr = 0;
-                    while (nr < YJ && j0 + nr < Ny) {
+                    while (nr < YJ && j0 + nr < Ny && !run_row[f][j0 + nr]) {
                         const int r2 = run_len(j0 + nr);
                         if (yrec_on && nr > 0 && FP.N_y_row[j0 + nr] >= Y_REC_MIN_N && r2 >= YJ) break;
                         nr += std::min(r2, YJ - nr);
@@ -404,9 +533,11 @@ void build_device(dfb_filter_s& H) {
                 std::stable_sort(all.begin(), all.end(), [](const YGroup& a, const YGroup& b) { return a.j0 < b.j0; });
                 groups.insert(groups.end(), all.begin(), all.end());
                 const int ng = (int)all.size();
-                for (int gb = 0; gb < ng; gb += Y_G) {
+                for (int gb = 0; gb < ng;) {
                     YTile t{};
-                    t.field = f; t.g0 = first_group + gb; t.ngroups = std::min(Y_G, ng - gb);
+                    int cnt = 1;                                      // up to Y_G groups that are adjacent in the plane
+                    while (cnt < Y_G && gb + cnt < ng && all[gb + cnt].j0 == all[gb + cnt - 1].j0 + all[gb + cnt - 1].nrows) ++cnt;
+                    t.field = f; t.g0 = first_group + gb; t.ngroups = cnt;
                     t.cbegin = 1 << 30; t.cend = 0;
                     for (int w = 0; w < t.ngroups; ++w) {
                         const YGroup& g = groups[t.g0 + w];
@@ -415,6 +546,7 @@ void build_device(dfb_filter_s& H) {
                     }
                     const int step = yrec_on ? Y_TK : ytk;
                     for (int c0 = 0; c0 < D.f[f].We; c0 += step) { t.col0 = c0; (yrec_on ? tiles_rec : tiles_dense).push_back(t); }
+                    gb += cnt;
                 }
             }
         }
@@ -450,88 +582,21 @@ void build_device(dfb_filter_s& H) {
         H.yp[0].prof = H.dalloc<unsigned long long>(8);
         if (std::getenv("DFB_TIMELINE")) { H.tl = H.dalloc<unsigned long long>(512); timeline_reset(H); }
         H.yp[0].debug = std::getenv("DFB_DEBUG_Y") ? std::atoi(std::getenv("DFB_DEBUG_Y")) : 0;
-        H.y_form = yrec_on ? 1 : 0;
-        {
-            // Run-recursive form (ysweep_run_kernel, the default): rows cut into groups of <= YJ consecutive rows of ONE half-width,
-            // never across a block of RB rows; a block x 32 columns = one tile whose whole window is staged in shared memory.
-            // RB = 128 when two such windows fit (fewest re-reads of the overlapping windows), else 64, else 32.
-            cudaDeviceProp prop;
-            CUDA_TRY(cudaGetDeviceProperties(&prop, H.device));
-            bool use_run = false;
-            std::vector<YRGroup> rg;
-            std::vector<YRTile> rt;
-            int wrows_max = 0;
-            int nbuf = 2;
-            const int trials[6][2] = {{128, 2}, {64, 2}, {32, 2}, {128, 1}, {64, 1}, {32, 1}};      // (rows per block, window buffers)
-            for (const auto& tr : trials) {
-                const int RB = tr[0];
-                nbuf = tr[1];
-                rg.clear(); rt.clear(); wrows_max = 0;
-                for (int f = 0; f < 3; ++f) {
-                    const FieldPlan& FP = P.f[f];
-                    for (int jb = 0; jb < Ny; jb += RB) {
-                        const int je = std::min(Ny, jb + RB);
-                        std::vector<YRGroup> blk;
-                        for (int j0 = jb; j0 < je;) {
-                            const int N = FP.N_y_row[j0];
-                            int R = 1;
-                            while (j0 + R < je && R < YJ && FP.N_y_row[j0 + R] == N) ++R;
-                            YRGroup g{};
-                            g.j0 = j0; g.nrows = R; g.N = N;
-                            if (N >= 1) {
-                                const long double a = (long double)std::exp(-2.0 * 3.14159265358979323846 * 1.0 / N);
-                                g.a = (double)a;
-                                g.a4 = (double)(a * a * a * a);
-                                g.naN1 = -(double)std::pow(a, (long double)(N + 1));
-                            }
-                            g.inv_s = *P.coef.centre(N);
-                            blk.push_back(g);
-                            j0 += R;
-                        }
-                        std::stable_sort(blk.begin(), blk.end(), [](const YRGroup& x, const YRGroup& y) { return 2 * x.N + 4 * x.nrows > 2 * y.N + 4 * y.nrows; });
-                        YRTile t{};
-                        t.field = f; t.g0 = (int)rg.size(); t.ngroups = (int)blk.size();
-                        int lo = 1 << 30, hi = -1;
-                        for (const YRGroup& g : blk) {
-                            lo = std::min(lo, g.j0 + FP.Ny_max - g.N);
-                            hi = std::max(hi, g.j0 + g.nrows - 1 + FP.Ny_max + g.N);
-                        }
-                        t.wlo = lo; t.wrows = hi - lo + 1;
-                        wrows_max = std::max(wrows_max, round_up(t.wrows, YR_BOX));
-                        rg.insert(rg.end(), blk.begin(), blk.end());
-                        for (int c0 = 0; c0 < D.f[f].We; c0 += YR_C) { t.col0 = c0; rt.push_back(t); }
-                    }
-                }
-                if (ysweep_run_smem(wrows_max, nbuf) <= (size_t)prop.sharedMemPerBlockOptin) { use_run = true; break; }
-            }
-            // Two windows per CTA when they fit (N_y up to ~190 with 32-row blocks), else one (N_y up to ~400; the reference's default
-            // plane, N_y = 212, runs 128-row blocks this way); beyond that the band-matrix kernels stream the windows
-            // ... and only where it pays: where the half-width changes from row to row (the steep part of the reference's default
-            // plane: runs of one or two rows, N_y up to 212) a group of one row costs as much as the direct sum and the tall windows
-            // leave room for one buffer only -- measured there: 42 us against 32 us for the dense band matrices.  Run form when it
-            // executes less than half of the direct sum's multiply-adds and two windows fit; DFB_Y_MODE=2 forces it wherever it fits.
-            {
-                double c_run = 0, c_dense = 0;
-                for (const YRGroup& g : rg) c_run += 2.0 * (g.N + 1) + 4.0 * g.nrows;
-                for (int f = 0; f < 3; ++f) for (int v : P.f[f].N_y_row) c_dense += 2.0 * v + 1.0;
-                const bool fits = use_run;
-                use_run = fits && nbuf == 2 && c_run < 0.5 * c_dense;
-                if (const char* ym = std::getenv("DFB_Y_MODE")) use_run = std::atoi(ym) == 2 && fits;
-            }
-            if (use_run) {
-                // most expensive tiles first; the persistent CTAs take them round-robin
-                auto cost = [&](const YRTile& t) { long long c = 0; for (int g = 0; g < t.ngroups; ++g) c += 2 * rg[t.g0 + g].N + 4 * rg[t.g0 + g].nrows + 8; return c; };
-                std::stable_sort(rt.begin(), rt.end(), [&](const YRTile& x, const YRTile& y) { return cost(x) > cost(y); });
-                H.y_form = 2;
-                H.yp[0].rgroups = H.upload(rg);
-                H.yp[0].rtiles = H.upload(rt);
-                H.yp[0].n_rtiles = (int)rt.size();
-                H.yp[0].r_wrows = wrows_max;
-                H.yp[0].r_nbuf = nbuf;
-                H.yp[0].r_smem = (int)ysweep_run_smem(wrows_max, nbuf);
-                H.yp[0].r_grid = prop.multiProcessorCount;
-                CUDA_TRY(ysweep_run_prepare((size_t)H.yp[0].r_smem));
-            }
+        // form of the y-sweep: 0 dense band matrices, 1 chunk-recursive band matrices, 2 run-recursive, 3 both (run form on the row
+        // blocks where it pays, dense band matrices on the rest)
+        H.y_form = any_run ? (any_band ? 3 : 2) : (yrec_on ? 1 : 0);
+        if (any_run) {
+            // most expensive tiles first; the persistent CTAs take them round-robin
+            auto cost = [&](const YRTile& t) { long long c = 0; for (int g = 0; g < t.ngroups; ++g) c += 2 * rg[t.g0 + g].N + 4 * rg[t.g0 + g].nrows + 8; return c; };
+            std::stable_sort(rt.begin(), rt.end(), [&](const YRTile& x, const YRTile& y) { return cost(x) > cost(y); });
+            H.yp[0].rgroups = H.upload(rg);
+            H.yp[0].rtiles = H.upload(rt);
+            H.yp[0].n_rtiles = (int)rt.size();
+            H.yp[0].r_wrows = r_wrows;
+            H.yp[0].r_nbuf = r_nbuf;
+            H.yp[0].r_smem = (int)ysweep_run_smem(r_wrows, r_nbuf);
+            H.yp[0].r_grid = yprop.multiProcessorCount;
+            CUDA_TRY(ysweep_run_prepare((size_t)H.yp[0].r_smem));
         }
         H.yp[1] = H.yp[0];
         H.yp[1].D = H.D[1];
@@ -548,7 +613,7 @@ void build_device(dfb_filter_s& H) {
                                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) throw Error{DFB_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")"};
         }
-        if (H.y_form == 2)
+        if (H.y_form >= 2)
             for (int b = 0; b < 2; ++b)
                 for (int f = 0; f < 3; ++f) {
                     const FieldDev& F = H.D[b].f[f];
@@ -816,8 +881,11 @@ void run_step(dfb_filter_s& H, double dt, bool first) {
     if (H.timing) CUDA_TRY(cudaEventRecord(H.ev[1], H.stream));
     if (H.noise_mode == DFB_NOISE_GENERATE && H.ybuf_step[b] == H.step) {
         // this step's y-sweep already ran (or is running) on the side stream; ev_noise[b] above covers it
-    } else if (H.tuned && H.y_form == 2) CUDA_TRY(launch_ysweep_run(H.rmaps[b], H.yp[b], H.stream));
-    else if (H.tuned) CUDA_TRY(launch_ysweep_tma(H.maps[b], H.yp[b], H.n_tiles_dense, H.n_tiles_rec, H.stream));
+    } else if (H.tuned) {
+        // band-matrix tiles (if any) first, then the run-recursive tiles: disjoint rows of r_zs
+        if (H.y_form != 2) CUDA_TRY(launch_ysweep_tma(H.maps[b], H.yp[b], H.n_tiles_dense, H.n_tiles_rec, H.stream));
+        if (H.y_form >= 2) CUDA_TRY(launch_ysweep_run(H.rmaps[b], H.yp[b], H.stream));
+    }
     else CUDA_TRY(launch_ysweep_simple(H.D[b], H.stream));
     if (H.timing) CUDA_TRY(cudaEventRecord(H.ev[2], H.stream));
     StepConsts S{};
@@ -851,8 +919,8 @@ void run_step(dfb_filter_s& H, double dt, bool first) {
         // ... and so does its y-sweep (it reads only that noise and writes only that set's r_zs interior): it
         // becomes resident as this step's z-sweep CTAs retire and keeps the fp64 pipe busy through the tail.
         if (H.tuned && H.y_ahead) {
-            if (H.y_form == 2) CUDA_TRY(launch_ysweep_run(H.rmaps[nb], H.yp[nb], H.side));
-            else CUDA_TRY(launch_ysweep_tma(H.maps[nb], H.yp[nb], H.n_tiles_dense, H.n_tiles_rec, H.side));
+            if (H.y_form != 2) CUDA_TRY(launch_ysweep_tma(H.maps[nb], H.yp[nb], H.n_tiles_dense, H.n_tiles_rec, H.side));
+            if (H.y_form >= 2) CUDA_TRY(launch_ysweep_run(H.rmaps[nb], H.yp[nb], H.side));
             CUDA_TRY(cudaEventRecord(H.ev_noise[nb], H.side));      // "set nb is ready" now means noise + y-sweep
             H.ybuf_step[nb] = H.step;
         }

@@ -111,8 +111,9 @@ int dfb_dims(dfb_handle h, int* Ny, int* Nz);
  * 4 algorithmic tap-FMAs per step (as int64 via out64), 5 global Nz, 6 CUDA device ordinal,
  * 7 form of the z-sweep in use: 1 = recursive evaluation of the exponential window, 0 = direct Toeplitz sum,
  * 8 / 9 y-sweep tiles of the band-matrix kernels evaluated recursively / with dense band matrices,
- * 10 form of the y-sweep in use: 2 = run-recursive (every row group through the exponential window, the default), 1 = chunk-recursive
- *    band-matrix kernel, 0 = dense band matrices (DFB_Y_MODE forces a form), 11 tiles of the run-recursive kernel, 12 transport of the config-4 hand-off: 2 = peer-to-peer copies (CUDA IPC + copy engines), 1 = NCCL
+ * 10 form of the y-sweep in use: 2 = run-recursive (every row group through the exponential window), 3 = run-recursive on the blocks of
+ *    32 rows where it pays + dense band matrices on the rest (e.g. the reference's default plane), 1 = chunk-recursive band-matrix
+ *    kernel, 0 = dense band matrices (DFB_Y_MODE=0|1|2 forces a form), 11 tiles of the run-recursive kernel, 12 transport of the config-4 hand-off: 2 = peer-to-peer copies (CUDA IPC + copy engines), 1 = NCCL
  *    send/recv, 0 = no communicator */
 int dfb_info(dfb_handle h, int what, int field, int64_t* out64);
 /* host copies of the setup tables (for parity tests): which = 0..7 rows R11,R21,R22,R33,Us,Ts,rhos,Ms [Ny];

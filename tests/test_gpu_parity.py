@@ -916,3 +916,20 @@ def test_N3_face_map_and_scatter_through_it(dfb, W):
     assert np.all(claimed == 1)
     assert np.array_equal(ghost.cpu().numpy(), whole.u.fluc[jj, kk])
     whole.close()
+
+
+def test_G2_hybrid_y_sweep_run_blocks_and_band_matrices(dfb, O, W):
+    """A plane whose half-widths are steady over most rows (run-recursive form pays) but change every row in a steep part (it does not):
+    the y-sweep runs BOTH forms, each on its own row blocks (dfb_info 10 == 3) -- against the oracle, every output."""
+    Ny, Nz = 320, 3400                                                  # wide enough for the run part to be worth a launch of its own
+    steep = np.arange(40, 104, 1) * 2                                   # N = 80, 82, ..., 206: a new half-width every row
+    row_N = np.concatenate([np.full(96, 40), steep, np.repeat(np.arange(100, 36, -4) * 2, 10)])[:Ny]
+    plane = _explicit_plane(W, Ny, Nz, [row_N, np.full(Ny, 24), row_N[::-1].copy()], [np.full(Ny, 6)] * 3)
+    cfg = dfb.DFConfig.from_plane(plane, noise_mode=dfb.NOISE_INJECT)
+    cfg.geom_per_row = 0
+    cfg.yc = cfg.dy = cfg.dz = None
+    cfg.N_y, cfg.N_z = plane["N_y"], plane["N_z"]
+    probe = dfb.DIGITAL_FILTER(cfg)
+    assert probe.tuned and probe.info(10) == 3, probe.info(10)
+    probe.close()
+    assert _run_explicit(dfb, O, plane, seed=29, dts=[3e-7])
