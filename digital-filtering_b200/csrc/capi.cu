@@ -266,7 +266,7 @@ void build_device(dfb_filter_s& H) {
         std::vector<YTile> tiles;
         std::vector<double> cmat;
         // ---- which rows go through the run-recursive form (ysweep_run_kernel), which through the band matrices ----
-        // The run form evaluates a group of R <= 8 rows of ONE half-width N with 2(N+1) + 4R multiply-adds per column where the direct sum
+        // The run form evaluates a group of R rows (<= 8, or <= min(32, 0.33 N) for N >= 25) of ONE half-width N with 2(N+1) + 4R multiply-adds per column where the direct sum
         // spends R(2N+1): it pays in runs of equal N, not where N changes every row or two (a lone row costs its direct sum and
         // its window has to be staged whole).  Decided per block of 32 rows: run form where it executes less than half of the
         // direct sum's multiply-adds (and two of the block's windows fit in shared memory); the other rows keep the band matrices.
@@ -280,6 +280,7 @@ void build_device(dfb_filter_s& H) {
         int r_wrows = 0, r_nbuf = 2;
         {
             constexpr int CB = 32;                                   // classification block
+            std::vector<int> cheap[3];                               // band-matrix blocks whose rows are cheap in either form
             for (int f = 0; f < 3; ++f) {
                 const std::vector<int>& Nr = P.f[f].N_y_row;
                 run_row[f].assign(Ny, 0);
@@ -289,7 +290,8 @@ void build_device(dfb_filter_s& H) {
                     double c_run = 0, c_dense = 0;
                     for (int j = jb; j < je;) {
                         int R = 1;
-                        while (j + R < je && R < YJ && Nr[j + R] == Nr[j]) ++R;
+                        const int cap = yr_group_cap(Nr[j]);
+                        while (j + R < je && R < cap && Nr[j + R] == Nr[j]) ++R;
                         c_run += 2.0 * (Nr[j] + 1) + 4.0 * R;
                         for (int t = 0; t < R; ++t) c_dense += 2.0 * Nr[j + t] + 1.0;
                         j += R;
@@ -297,12 +299,21 @@ void build_device(dfb_filter_s& H) {
                     // ... and only where a 128-row block of such rows fits twice into shared memory (N up to ~150): taller windows force
                     // short blocks, which re-read their windows many times over (measured on the reference's default plane, N_y up to
                     // 212: 32-row blocks with 400-row windows made the y-sweep slower than the band matrices alone)
-                    int Nm = 0;
-                    for (int j = jb; j < je; ++j) Nm = std::max(Nm, Nr[j]);
+                    int Nm = 0, Nmin = 1 << 30;
+                    for (int j = jb; j < je; ++j) { Nm = std::max(Nm, Nr[j]); Nmin = std::min(Nmin, Nr[j]); }
                     const bool roomy = ysweep_run_smem(round_up(128 + 2 * Nm, YR_BOX), 2) <= (size_t)yprop.sharedMemPerBlockOptin;
                     if (ymode_env == 2 || (c_run < 0.5 * c_dense && roomy)) std::fill(run_row[f].begin() + jb, run_row[f].begin() + je, 1);
+                    else if (ymode_env < 0 && Nmin >= 1 && c_dense < 48.0 * (je - jb)) cheap[f].push_back(jb);
                 }
             }
+            // Blocks of small half-widths (N below ~24, near the wall) cost next to nothing in either form: where the plane runs the
+            // run form anyway they join it, so that a plane is not split into two launches for their sake (1024x2048 profile:
+            // 0.113 -> 0.109 ms/step)
+            bool some_run = false;
+            for (int f = 0; f < 3; ++f) some_run = some_run || std::count(run_row[f].begin(), run_row[f].end(), 1) > 0;
+            if (some_run)
+                for (int f = 0; f < 3; ++f)
+                    for (int jb : cheap[f]) std::fill(run_row[f].begin() + jb, run_row[f].begin() + std::min(Ny, jb + CB), 1);
             // run plan over the run rows: maximal contiguous ranges chopped into blocks of RB rows; a block x 32 columns = one tile
             auto build = [&](int RB) {
                 rg.clear(); rt.clear();
@@ -319,9 +330,10 @@ void build_device(dfb_filter_s& H) {
                             for (int j0 = jb; j0 < je;) {
                                 const int N = FP.N_y_row[j0];
                                 int R = 1;
-                                while (j0 + R < je && R < YJ && FP.N_y_row[j0 + R] == N) ++R;
+                                const int cap = yr_group_cap(N);
+                                while (j0 + R < je && R < cap && FP.N_y_row[j0 + R] == N) ++R;
                                 YRGroup g{};
-                                g.j0 = j0; g.nrows = R; g.N = N;
+                                g.j0 = j0; g.nrows = R; g.N = N; g.pad = R > YJ ? 1 : 0;
                                 if (N >= 1) {
                                     const long double a = (long double)std::exp(-2.0 * 3.14159265358979323846 * 1.0 / N);
                                     g.a = (double)a;
@@ -384,7 +396,10 @@ void build_device(dfb_filter_s& H) {
         // Both forms on one plane = two y-sweep launches per step; that only pays when the run-recursive part has enough tiles to
         // fill the machine a few times over (measured on the reference's default plane: alone 49.6 us per step against 42.5 with the
         // band matrices only; as a batch of 8 planes 20.8 us per plane-step against 23.8)
-        if (any_run && any_band && ymode_env < 0 && (long long)rt.size() * NP < 4ll * yprop.multiProcessorCount) {
+        // (counted on the WHOLE plane's width, so that every slab of a plane takes the decision the plane itself would take)
+        long long run_tiles_plane = 0;
+        for (const YRTile& t : rt) if (t.col0 == 0) run_tiles_plane += (NzG + YR_C - 1) / YR_C;
+        if (any_run && any_band && ymode_env < 0 && run_tiles_plane * NP < 4ll * yprop.multiProcessorCount) {
             for (int f = 0; f < 3; ++f) run_row[f].assign(Ny, 0);
             rg.clear(); rt.clear();
             any_run = false;
@@ -586,9 +601,24 @@ void build_device(dfb_filter_s& H) {
         // blocks where it pays, dense band matrices on the rest)
         H.y_form = any_run ? (any_band ? 3 : 2) : (yrec_on ? 1 : 0);
         if (any_run) {
-            // most expensive tiles first; the persistent CTAs take them round-robin
+            // most expensive tiles first; the persistent CTAs take them round-robin.  A tile's window overlaps those of the row blocks
+            // above and below it (block + 2 N rows): while the sweep's whole input fits in L2 (126 MB) the re-reads are served from
+            // there; a larger plane (4096x8192: 0.8 GB) is walked in groups of a few 32-column tiles -- every row block of every field
+            // of the group, most expensive first, before the next group -- so that the overlapping rows are still in L2 when the
+            // neighbouring block asks for them.  (The order of the tiles does not enter any cell's arithmetic.)
             auto cost = [&](const YRTile& t) { long long c = 0; for (int g = 0; g < t.ngroups; ++g) c += 2 * rg[t.g0 + g].N + 4 * rg[t.g0 + g].nrows + 8; return c; };
-            std::stable_sort(rt.begin(), rt.end(), [&](const YRTile& x, const YRTile& y) { return cost(x) > cost(y); });
+            size_t in_bytes = 0, coltile_bytes = 0;
+            for (int f = 0; f < 3; ++f) {
+                in_bytes += (size_t)NP * D.f[f].ps_ys * sizeof(double);
+                coltile_bytes += (size_t)NP * D.f[f].rows_y * YR_C * sizeof(double);
+            }
+            int colgroup = 1 << 30;                                   // 32-column tiles per group: everything in one group
+            if (in_bytes > ((size_t)96 << 20)) colgroup = (int)std::max<size_t>(1, ((size_t)16 << 20) / coltile_bytes);
+            if (const char* e = std::getenv("DFB_Y_COLGROUP")) colgroup = std::max(1, std::atoi(e));
+            std::stable_sort(rt.begin(), rt.end(), [&](const YRTile& x, const YRTile& y) {
+                const int gx = x.col0 / YR_C / colgroup, gy = y.col0 / YR_C / colgroup;
+                return gx != gy ? gx < gy : cost(x) > cost(y);
+            });
             H.yp[0].rgroups = H.upload(rg);
             H.yp[0].rtiles = H.upload(rt);
             H.yp[0].n_rtiles = (int)rt.size();

@@ -73,7 +73,12 @@ struct YTile {                 // up to Y_G consecutive groups x Y_TK columns
 
 struct YMaps { CUtensorMap m[3]; };
 
-// ---- y-sweep, run-recursive form (ysweep_run_kernel): row groups of <= YJ consecutive rows with ONE half-width ----
+// ---- y-sweep, run-recursive form (ysweep_run_kernel): row groups of consecutive rows with ONE half-width ----
+constexpr int YR_JL = 32;      // most rows of a long (lock-step) group; short groups hold <= YJ rows
+constexpr int YR_LOCK_MIN_N = 25;
+// Most rows a group of half-width N may hold.  Long groups walk the B sum against its stable direction (an error grows by
+// 1/a = exp(2 pi / N) per row): bounded so that exp(2 pi R / N) <= 8, i.e. R <= N ln 8 / (2 pi) = 0.331 N.
+inline int yr_group_cap(int N) { return N >= YR_LOCK_MIN_N ? (N * 331 / 1000 < YR_JL ? N * 331 / 1000 : YR_JL) : YJ; }
 constexpr int YR_C = 32;       // columns per tile = lanes of a warp (one column each)
 constexpr int YR_BOX = 32;     // padded rows per TMA box of the resident window
 #ifndef YR_CONSUMERS_N
@@ -84,7 +89,7 @@ constexpr int YR_CONSUMERS = YR_CONSUMERS_N;   // consumer warps of the persiste
                                                // fewer warps leave free go to the next step's noise CTAs, which run beside it
 constexpr int YR_MAXG = 128;   // most groups a tile can hold (a block of 128 rows, every row its own group)
 struct YRGroup {               // 48 bytes
-    int j0, nrows, N, pad;
+    int j0, nrows, N, pad;     // pad: 1 = long group (nrows > YJ), evaluated in lock step
     double a;                  // exp(-2 pi / N): ratio of neighbouring coefficients, b_i = a^|i| / s (df.cpp:168-177); 0 for N = 0
     double a4;                 // a^4 (the Horner starts run as four interleaved chains)
     double naN1;               // -a^(N+1): weight of the sample a sliding window drops

@@ -582,10 +582,12 @@ __global__ void __launch_bounds__(160, 3) ysweep_rec_kernel(const __grid_constan
 //     out_j = (F_j + B_j - x_j) / s,   F_j = sum_{i=0..N} a^i x_{j-i},   B_j = sum_{i=0..N} a^i x_{j+i},
 // and inside a run of rows that share N both sums slide:  F_{j+1} = a F_j + x_{j+1} - a^(N+1) x_{j-N},
 // B_{j-1} = a B_j + x_{j-1} - a^(N+1) x_{j+N}.  The half-width changes every few rows on boundary-layer grids, so the
-// rows are cut into groups of <= 8 consecutive rows of ONE half-width (a lone row is a group of one); per group and
-// column: two Horner starts over N+1 samples each (run as four interleaved chains in a^4 per side: eight independent
-// FMA chains per thread) + 4 FMAs per further row -- 2(N+1) + 4R - 2 FMAs where the direct sum spends R(2N+1); 5x fewer
-// on the 1024x2048 boundary-layer profile, and no zero-padded band matrices at all.
+// rows are cut into groups of consecutive rows of ONE half-width (a lone row is a group of one): up to 8 rows, F walking
+// up from the first row and B down from the last, or -- N >= 25, runs longer than 8 -- up to min(32, 0.33 N) rows with
+// both sums walking in lock step from the first row.  Per group and column: two Horner starts over N+1 samples each
+// (run as four interleaved chains in a^4 per side: eight independent FMA chains per thread) + 4 FMAs per further row
+// -- 2(N+1) + 4R - 2 FMAs where the direct sum spends R(2N+1); 5x fewer on the 1024x2048 boundary-layer profile, and no
+// zero-padded band matrices at all.
 //
 // One tile = a block of up to 128 output rows x 32 columns of one field: its whole input window (block + 2 N_max rows)
 // is staged ONCE in shared memory by TMA (32-row boxes of cp.async.bulk.tensor.2d), 256 bytes per row: a warp reads one
@@ -667,7 +669,8 @@ __global__ void __launch_bounds__(32 * (YR_CONSUMERS + 1), 1) ysweep_run_kernel(
             const int R = G.nrows, N = G.N;
             const double a = G.a, a4 = G.a4, naN1 = G.naN1, inv_s = G.inv_s;
             const int c = G.j0 + F.Ny_max - wlo;                 // window row of the group's first output row
-            const int ct = c + R - 1;                            // ... of its last
+            const bool lock = G.pad != 0;                        // long group: both sums walk down from the first row (below)
+            const int ct = lock ? c : c + R - 1;                 // row the B sum starts at: the group's last row, or its first
             // ---- Horner starts: F at the first row over rows c-N..c, B at the last row over rows ct..ct+N; term i = 4 m + q goes to chain q ----
             double f0 = 0.0, f1 = 0.0, f2 = 0.0, f3 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
             {
@@ -705,7 +708,35 @@ __global__ void __launch_bounds__(32 * (YR_CONSUMERS + 1), 1) ysweep_run_kernel(
             }
             double Fc = __fma_rn(a, __fma_rn(a, __fma_rn(a, f3, f2), f1), f0);
             double Bc = __fma_rn(a, __fma_rn(a, __fma_rn(a, b3, b2), b1), b0);
-            // ---- walks over the group's rows ----
+            double* dst = F.r_zs + (size_t)pl * F.ps_zs + (size_t)G.j0 * F.pitch_z + F.zoff + F.yshift + x;   // r_zs interior (df.cpp:377)
+            if (lock) {
+                // ---- long group (9..YR_JL rows, N >= 25): F and B both start at the first row and walk down in lock step, ----
+                //   F_{j+1} = a F_j + (x_{j+1} - a^(N+1) x_{j-N}),      B_{j+1} = B_j / a + (a^N x_{j+1+N} - x_j / a),
+                // nothing is kept per row, one dependent FMA per row and sum.  The B walk runs against its stable direction: an error
+                // grows by 1/a per row, so the planner bounds the group length by exp(2 pi R / N) <= 8 (R <= 0.33 N): measured
+                // deviation from the direct sum <= 2.5e-15 of the rms at the bound (gate 1e-12).
+                const double ia = __drcp_rn(a), aN = __dmul_rn(-naN1, ia);
+                double xc = col[c * YR_C];
+                {
+                    const double v = __dmul_rn(inv_s, __dsub_rn(__dadd_rn(Fc, Bc), xc));
+                    if (live) dst[0] = v;
+                }
+                const double* pc = col + (size_t)(c + 1) * YR_C;         // x_{j+1}
+                const double* pl_ = pc - (size_t)(N + 1) * YR_C;         // x_{j-N}
+                const double* ph = pc + (size_t)N * YR_C;                // x_{j+1+N}
+                double* d = dst + F.pitch_z;
+#pragma unroll 4
+                for (int tt = 1; tt < R; ++tt) {
+                    const double xn = *pc, xl = *pl_, xh = *ph;
+                    Fc = __fma_rn(a, Fc, __fma_rn(naN1, xl, xn));
+                    Bc = __fma_rn(ia, Bc, __fma_rn(aN, xh, -__dmul_rn(ia, xc)));
+                    const double v = __dmul_rn(inv_s, __dsub_rn(__dadd_rn(Fc, Bc), xn));
+                    if (live) *d = v;
+                    xc = xn;
+                    pc += YR_C; pl_ += YR_C; ph += YR_C; d += F.pitch_z;
+                }
+            } else {
+            // ---- walks over the group's rows: F up from the first row, B down from the last (both in their stable direction) ----
             double xr[YJ], Fv[YJ], xlo[YJ], xhi[YJ];
 #pragma unroll
             for (int tt = 0; tt < YJ; ++tt) {
@@ -719,7 +750,6 @@ __global__ void __launch_bounds__(32 * (YR_CONSUMERS + 1), 1) ysweep_run_kernel(
                 if (tt < R) Fc = __fma_rn(naN1, xlo[tt], __fma_rn(a, Fc, xr[tt]));
                 Fv[tt] = Fc;
             }
-            double* dst = F.r_zs + (size_t)pl * F.ps_zs + (size_t)G.j0 * F.pitch_z + F.zoff + F.yshift + x;   // r_zs interior (df.cpp:377)
 #pragma unroll
             for (int tt = YJ - 1; tt >= 0; --tt) {
                 if (tt < R) {
@@ -727,6 +757,7 @@ __global__ void __launch_bounds__(32 * (YR_CONSUMERS + 1), 1) ysweep_run_kernel(
                     const double v = __dmul_rn(inv_s, __dsub_rn(__dadd_rn(Fv[tt], Bc), xr[tt]));
                     if (live) dst[(size_t)tt * F.pitch_z] = v;
                 }
+            }
             }
             // next group of this tile
             int nx = 0;

@@ -465,10 +465,12 @@ def test_large_half_widths_beyond_128(dfb, O, W, monkeypatch, ymode):
 
 @pytest.mark.parametrize("ymode", ["2", "1", "0"], ids=["y-run-recursive", "y-chunk-recursive", "y-dense"])
 def test_G2_both_forms_of_the_y_sweep(dfb, O, W, monkeypatch, ymode):
-    """The tuned y-sweep has three forms: run-recursive (ysweep_run_kernel, the default: every group of <= 8 rows of one half-width
-    through the exponential window), and the band-matrix kernels kept for windows too tall for shared memory -- chunk-recursive
-    (ysweep_rec_kernel) and dense.  Each forced in turn, on a boundary-layer profile (N_y changes every few rows: runs of every length, mixed leftovers) and on hand-made runs
-    (lengths 1..20, N from 2 to 200, windows not aligned to the 8-row chunks), both must pass the gate."""
+    """The tuned y-sweep has three forms: run-recursive (ysweep_run_kernel, the default: every group of rows of one half-width
+    through the exponential window -- short groups of <= 8 rows, long lock-step groups of up to min(32, 0.33 N) rows), and the
+    band-matrix kernels kept for windows too tall for shared memory -- chunk-recursive (ysweep_rec_kernel) and dense.  Each forced
+    in turn, on a boundary-layer profile (N_y changes every few rows: runs of every length, mixed leftovers) and on hand-made runs
+    (lengths 1..40, N from 2 to 200, windows not aligned to the 8-row chunks; the third field one run of N = 128), all must pass
+    the gate."""
     monkeypatch.setenv("DFB_Y_MODE", ymode)
     probe = dfb.DIGITAL_FILTER(dfb.DFConfig.from_plane(W.plane_profile(200, 300, 96, 24), noise_mode=dfb.NOISE_INJECT))
     assert probe.info(10) == int(ymode)
@@ -477,8 +479,8 @@ def test_G2_both_forms_of_the_y_sweep(dfb, O, W, monkeypatch, ymode):
     assert max(worst.values()) < 1e-13, worst
     rng = np.random.default_rng(7)
     runs, Ns = [], [2, 8, 15, 16, 17, 18, 31, 40, 64, 66, 100, 128, 200]
-    while sum(runs) < 230:
-        runs.append(int(rng.integers(1, 21)))
+    while sum(runs) < 330:
+        runs.append(int(rng.integers(1, 41)))
     row_N = np.concatenate([np.full(r, Ns[int(rng.integers(0, len(Ns)))]) for r in runs])
     Ny, Nz = len(row_N), 150
     plane = _explicit_plane(W, Ny, Nz, [row_N, row_N[::-1].copy(), np.full(Ny, 128)], [np.full(Ny, 4)] * 3)
