@@ -281,6 +281,8 @@ void build_device(dfb_filter_s& H) {
         {
             constexpr int CB = 32;                                   // classification block
             std::vector<int> cheap[3];                               // band-matrix blocks whose rows are cheap in either form
+            double band_cost = 0, all_cost = 0;                      // direct-sum multiply-adds per column: band-matrix blocks, all blocks
+            bool band_convertible = true;                            // every band-matrix block could take the run form
             for (int f = 0; f < 3; ++f) {
                 const std::vector<int>& Nr = P.f[f].N_y_row;
                 run_row[f].assign(Ny, 0);
@@ -303,7 +305,12 @@ void build_device(dfb_filter_s& H) {
                     for (int j = jb; j < je; ++j) { Nm = std::max(Nm, Nr[j]); Nmin = std::min(Nmin, Nr[j]); }
                     const bool roomy = ysweep_run_smem(round_up(128 + 2 * Nm, YR_BOX), 2) <= (size_t)yprop.sharedMemPerBlockOptin;
                     if (ymode_env == 2 || (c_run < 0.5 * c_dense && roomy)) std::fill(run_row[f].begin() + jb, run_row[f].begin() + je, 1);
-                    else if (ymode_env < 0 && Nmin >= 1 && c_dense < 48.0 * (je - jb)) cheap[f].push_back(jb);
+                    else {
+                        if (ymode_env < 0 && Nmin >= 1 && c_dense < 48.0 * (je - jb)) cheap[f].push_back(jb);
+                        band_cost += c_dense;
+                        band_convertible = band_convertible && roomy && Nmin >= 1;
+                    }
+                    all_cost += c_dense;
                 }
             }
             // Blocks of small half-widths (N below ~24, near the wall) cost next to nothing in either form: where the plane runs the
@@ -314,6 +321,11 @@ void build_device(dfb_filter_s& H) {
             if (some_run)
                 for (int f = 0; f < 3; ++f)
                     for (int jb : cheap[f]) std::fill(run_row[f].begin() + jb, run_row[f].begin() + std::min(Ny, jb + CB), 1);
+            // ... and so do the band-matrix blocks altogether when they are a small part of the plane's work (< 15 % of the direct
+            // sum's multiply-adds) and all of them fit: the second launch costs more than the band matrices save on them
+            // (1024x2048 profile, 64 of 1024 rows where N_y climbs from 20 to 118: 0.113 -> 0.109 ms/step as one launch)
+            if (some_run && ymode_env < 0 && band_convertible && band_cost < 0.15 * all_cost)
+                for (int f = 0; f < 3; ++f) run_row[f].assign(Ny, 1);
             // run plan over the run rows: maximal contiguous ranges chopped into blocks of RB rows; a block x 32 columns = one tile
             auto build = [&](int RB) {
                 rg.clear(); rt.clear();
