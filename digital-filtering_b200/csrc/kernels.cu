@@ -665,6 +665,8 @@ __global__ void __launch_bounds__(32 * (YR_CONSUMERS + 1), 1) ysweep_run_kernel(
         const bool live = x < F.We;
         const int ngroups = t.ngroups, wlo = t.wlo;
         for (int g = warp; g < ngroups;) {
+            int nx = 0;
+            if (lane == 0) nx = atomicAdd(&ctl.next_group[s], 1);       // the group after this one: asked for now, looked at below
             const YRGroup& G = ctl.groups[s][g];
             const int R = G.nrows, N = G.N;
             const double a = G.a, a4 = G.a4, naN1 = G.naN1, inv_s = G.inv_s;
@@ -759,10 +761,7 @@ __global__ void __launch_bounds__(32 * (YR_CONSUMERS + 1), 1) ysweep_run_kernel(
                 }
             }
             }
-            // next group of this tile
-            int nx = 0;
-            if (lane == 0) nx = atomicAdd(&ctl.next_group[s], 1);
-            g = __shfl_sync(0xffffffffu, nx, 0);
+            g = __shfl_sync(0xffffffffu, nx, 0);                        // next group of this tile
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&ctl.empty[s]);
@@ -891,7 +890,8 @@ __global__ void __maxnreg__(MODE == 1 ? Z_REC_MAXNREG : 168) zsweep_epilogue_ker
 
     // Pipeline per unit n (buffer n & 1, barrier phase (n >> 1) & 1); an item is the three consecutive units u, v, w:
     //   top:    stage unit n+1 (the v unit of this pair, or the first unit of the next item, whose descriptors are already in shared
-    //           memory); at an item's first unit also claim the item after the next (atomic, result not awaited)
+    //           memory: lane 0, ~650 cycles -- 20 for the proxy fence, ~230 for descriptor reads + expect_tx, ~135 per TMA operation);
+    //           at an item's first unit also claim the item after the next (atomic, result not awaited)
     //   middle: tap loop of unit n
     //   bottom: epilogue of unit n; at an item's last unit fetch the descriptors of the newly claimed item into the slot just vacated
     int slot = 0, phase = 0;
@@ -902,13 +902,17 @@ __global__ void __maxnreg__(MODE == 1 ? Z_REC_MAXNREG : 168) zsweep_epilogue_ker
         const int* dcur = descs + slot * 16 + phase * 8;
         const bool last_phase = phase == unA - 1;
         const bool have_next = !last_phase || itemB < n_total;
-        if (phase == 0 && itemB < n_total && lane == 0) claim = atomicAdd(P.counter, 1);        // the item after the next: requested first,
-                                                                                                // its round trip hides behind everything below
         if (have_next && lane == 0) {
             unsigned char* nb = wbase + (size_t)((n + 1) & 1) * P.unit_bytes;
             const int* dnext = last_phase ? descs + (slot ^ 1) * 16 : dcur + 8;
             z_issue_unit(P, maps, dnext, last_phase ? plB : plA, nb, &bars[(n + 1) & 1]);
         }
+        // (The address is made to look lane-dependent: an atomic add on an address ptxas can prove uniform is turned into a
+        //  warp-aggregated atomic whose result is shuffled at once -- the warp would sit out the whole round trip to L2,
+        //  ~700 cycles per item, right here.)
+        const int zoff = lane & dcur[7];                    // == 0 (ZUnit::pad), but not to the compiler
+        if (phase == 0 && itemB < n_total && lane == 0)
+            claim = atomicAdd(P.counter + zoff, 1);         // the item after the next: its round trip hides behind the tap loop
         if (P.debug & 16) pa_stage += clock64() - ttop;                                           // staging the next unit (lane 0)
 
         const int j = dcur[0], c0 = dcur[1], f = dcur[2];
