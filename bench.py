@@ -37,7 +37,7 @@ DEFAULT_WORKLOAD = "1024x2048_profile_N128"
 SLAB_WORKLOAD = "4096x8192_profile_N128"
 METRIC = "inflow cell-updates/sec per filter() step"
 DT = 1e-7
-NCU_SUMMARY = os.path.join("profiles", "ncu_full_r02_summary.csv")
+NCU_SUMMARY = os.path.join("profiles", "ncu_full_r02b_summary.csv")
 
 
 def common_config(plane):
