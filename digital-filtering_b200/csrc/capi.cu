@@ -925,6 +925,7 @@ void run_step(dfb_filter_s& H, double dt, bool first) {
         // this step's y-sweep already ran (or is running) on the side stream; ev_noise[b] above covers it
     } else if (H.tuned) {
         // band-matrix tiles (if any) first, then the run-recursive tiles: disjoint rows of r_zs
+        H.yp[b].zcounter_init = 8 * H.zp[b].nblocks;               // the z-sweep's warps (4 per CTA) start on two fixed items each
         if (H.y_form != 2) CUDA_TRY(launch_ysweep_tma(H.maps[b], H.yp[b], H.n_tiles_dense, H.n_tiles_rec, H.stream));
         if (H.y_form >= 2) CUDA_TRY(launch_ysweep_run(H.rmaps[b], H.yp[b], H.stream));
     }
@@ -961,6 +962,7 @@ void run_step(dfb_filter_s& H, double dt, bool first) {
         // ... and so does its y-sweep (it reads only that noise and writes only that set's r_zs interior): it
         // becomes resident as this step's z-sweep CTAs retire and keeps the fp64 pipe busy through the tail.
         if (H.tuned && H.y_ahead) {
+            H.yp[nb].zcounter_init = 8 * H.zp[nb].nblocks;
             if (H.y_form != 2) CUDA_TRY(launch_ysweep_tma(H.maps[nb], H.yp[nb], H.n_tiles_dense, H.n_tiles_rec, H.side));
             if (H.y_form >= 2) CUDA_TRY(launch_ysweep_run(H.rmaps[nb], H.yp[nb], H.side));
             CUDA_TRY(cudaEventRecord(H.ev_noise[nb], H.side));      // "set nb is ready" now means noise + y-sweep
@@ -1581,8 +1583,8 @@ int dfb_debug_zprof(dfb_handle h, unsigned long long* out8) {
     return guarded([&] {
         CUDA_TRY(cudaStreamSynchronize(h->stream));
         if (!h->zp[0].prof) throw Error{DFB_ERR_STATE, "no profile buffer"};
-        CUDA_TRY(cudaMemcpy(out8, h->zp[0].prof, 128, cudaMemcpyDeviceToHost));      // 16 counters
-        CUDA_TRY(cudaMemset(h->zp[0].prof, 0, 128));
+        CUDA_TRY(cudaMemcpy(out8, h->zp[0].prof, 1024, cudaMemcpyDeviceToHost));     // 128 counters
+        CUDA_TRY(cudaMemset(h->zp[0].prof, 0, 1024));
     });
 }
 

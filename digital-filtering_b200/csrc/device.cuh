@@ -134,7 +134,8 @@ struct YParams {
     const YGroup* groups;
     const YTile* tiles;
     const double* cmat;
-    int* zcounter;             // work counter of the z-sweep that follows (reset here)
+    int* zcounter;             // work counter of the z-sweep that follows (reset here ...
+    int zcounter_init;         // ... to twice the z-sweep's warp count: its warps start on items they do not have to claim)
     const double* yrec;        // recursive groups, 16 doubles per half-width N: a at [0], a^2, a^4, a^8 at [10..12]
     const double* ygc;         // recursive groups, 16 doubles each: factors of the low-bulk sum [0..7] and of the high-bulk sum [8..15] per output row
     const YRGroup* rgroups;    // run-recursive form: groups and tiles (most expensive tile first), see ysweep_run_kernel

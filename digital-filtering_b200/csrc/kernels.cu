@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(160, 3) ysweep_tma_kernel(const __grid_constan
     if (threadIdx.x == 0) {
         for (int s = 0; s < NS; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], Y_G); }
         mbar_fence_init();
-        if (tix == 0 && P.zcounter) *P.zcounter = 0;      // the z-sweep that follows pulls its items from here
+        if (tix == 0 && P.zcounter) *P.zcounter = P.zcounter_init;      // the z-sweep that follows pulls its items from here
         tl_stamp(P.tl, 0);
     }
     __syncthreads();
@@ -424,7 +424,7 @@ __global__ void __launch_bounds__(160, 3) ysweep_rec_kernel(const __grid_constan
     if (threadIdx.x == 0) {
         for (int s = 0; s < NS; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], Y_G); }
         mbar_fence_init();
-        if (blockIdx.x == 0 && P.zcounter) *P.zcounter = 0;
+        if (blockIdx.x == 0 && P.zcounter) *P.zcounter = P.zcounter_init;
         tl_stamp(P.tl, 0);
     }
     __syncthreads();
@@ -621,7 +621,7 @@ __global__ void __launch_bounds__(32 * (YR_CONSUMERS + 1), 1) ysweep_run_kernel(
     if (threadIdx.x == 0) {
         for (int s = 0; s < 2; ++s) { mbar_init(&ctl.full[s], 1); mbar_init(&ctl.empty[s], YR_CONSUMERS); }
         mbar_fence_init();
-        if (blockIdx.x == 0 && P.zcounter) *P.zcounter = 0;      // the z-sweep that follows pulls its items from here
+        if (blockIdx.x == 0 && P.zcounter) *P.zcounter = P.zcounter_init;      // the z-sweep that follows pulls its items from here
         tl_stamp(P.tl, 0);
     }
     __syncthreads();
@@ -866,6 +866,8 @@ __global__ void __maxnreg__(MODE == 1 ? Z_REC_MAXNREG : 168) zsweep_epilogue_ker
 
     if (lane == 0) tl_stamp(P.tl, 0);
     const long long tstart = (P.debug & 16) ? clock64() : 0;
+    unsigned long long gstart = 0;
+    if (P.debug & 16) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gstart));
     // Items: first the (u, v) pairs -- two units back to back, v picks u's blended strip up from the warp's line buffer --, then the w
     // units as items of their own (the queue's tail is then one unit long, not three).  Item it of a plane: units [off, off + nun).
     const int nP = D.P, n_total = P.n_items * nP;
@@ -874,14 +876,14 @@ __global__ void __maxnreg__(MODE == 1 ? Z_REC_MAXNREG : 168) zsweep_epilogue_ker
     auto fetch_item = [&](int g) {                          // the item's unit descriptors, one int per lane (16 or 8 lanes)
         return lane < 8 * item_units(g) ? __ldg(reinterpret_cast<const int*>(P.units + item_off(g)) + lane) : 0;
     };
-    // claim the first two items; stage the first unit
+    // The first two items of every warp are fixed -- items are sorted most expensive first, warp g of G takes g and G + g -- and
+    // the counter starts at 2 G (set by the y-sweep): no warp begins with two round trips to one contended L2 address.
+    const int gw = (int)blockIdx.x * 4 + warp, gwarps = (int)gridDim.x * 4;
     int claim = 0;
-    if (lane == 0) claim = atomicAdd(P.counter, 1);
-    int itemA = __shfl_sync(0xffffffffu, claim, 0);
+    int itemA = gw;
     if (itemA >= n_total) return;
     if (lane < 16) descs[lane] = fetch_item(itemA);
-    if (lane == 0) claim = atomicAdd(P.counter, 1);
-    int itemB = __shfl_sync(0xffffffffu, claim, 0);
+    int itemB = gw + gwarps;
     if (itemB < n_total && lane < 16) descs[16 + lane] = fetch_item(itemB);
     __syncwarp();
     int plA = itemA % nP, plB = itemB % nP;                 // plane of a batch (0 for a single plane), kept per item: no division per unit
@@ -1221,6 +1223,15 @@ __global__ void __maxnreg__(MODE == 1 ? Z_REC_MAXNREG : 168) zsweep_epilogue_ker
                 atomicAdd(P.prof + 5, life);
                 atomicMax(P.prof + 6, life);
                 atomicAdd(P.prof + 7, 1ull);
+                // start / end of this warp on the global nanosecond timer: [10] latest start, [11] earliest start (as 2^62 - t),
+                // [12] latest end, [13] earliest end (as 2^62 - t), [14] sum of ends - starts
+                unsigned long long gend;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gend));
+                atomicMax(P.prof + 10, gstart); atomicMax(P.prof + 11, (1ull << 62) - gstart);
+                atomicMax(P.prof + 12, gend);   atomicMax(P.prof + 13, (1ull << 62) - gend);
+                atomicAdd(P.prof + 14, gend - gstart);
+                atomicAdd(P.prof + 16 + min(63, (int)((gend - gstart) / 1000)), 1ull);       // [16..79] histogram of warp lifetimes, 1 us bins
+                atomicAdd(P.prof + 80 + min(31, (int)pa_n), 1ull);                           // [80..111] histogram of units per warp
             }
             break;
         }
