@@ -7,7 +7,9 @@ import _dfb_import, digital_filtering_b200 as dfb
 from digital_filtering_b200 import workloads as W
 names = sys.argv[1:] or ["1024x2048_profile_N128", "1024x2048_saturated_N128", "4096x8192_profile_N128"]
 for name in names:
-    df = dfb.DIGITAL_FILTER(dfb.DFConfig.from_plane(W.NAMED[name](), seed=1), fetch=False)
+    # a name like profile:1024:2048:128:64 is W.plane_profile(Ny, Nz, max N_y, max N_z)
+    plane = W.plane_profile(*map(int, name.split(":")[1:])) if name.startswith("profile:") else W.NAMED[name]()
+    df = dfb.DIGITAL_FILTER(dfb.DFConfig.from_plane(plane, seed=1), fetch=False)
     st = torch.cuda.ExternalStream(df.stream())
     for _ in range(30): df.filter(1e-7)
     df.sync()
