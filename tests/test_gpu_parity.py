@@ -773,6 +773,9 @@ def test_config5_batch_equals_independent_handles_bitwise(dfb, W, shape):
     batch = dfb.DIGITAL_FILTER(dfb.DFConfig.from_plane(plane, seed=9, plane_id=3), nplanes=P)
     singles = [dfb.DIGITAL_FILTER(dfb.DFConfig.from_plane(plane, seed=9, plane_id=3 + p), fetch=False) for p in range(P)]
     sel = (dfb.U_FLUC, dfb.V_FLUC, dfb.W_FLUC, dfb.T_FLUC, dfb.RHO_FLUC, dfb.U_FILT, dfb.V_FILT, dfb.W_FILT)
+    # bit-identity holds between handles that run the same form of the y-sweep (a batch has P times the tiles and may take the
+    # run form where a single plane would not; DFB_Y_MODE pins it)
+    assert batch.info(10) == singles[0].info(10), (batch.info(10), singles[0].info(10))
     for s, dt in enumerate([None, 1e-7, 3e-7, 1e-7]):
         if dt is not None:
             batch.filter(dt)
