@@ -802,6 +802,32 @@ def test_config5_batch_equals_independent_handles_bitwise(dfb, W, shape):
         d.close()
 
 
+def test_config5_default_plane_batch_against_single_plane(dfb, O):
+    """BASELINE config 5 proper: 8 planes of the reference's default geometry behind one handle.  The batch has 8 times the tiles
+    and takes the run-recursive y-sweep on the row blocks where it pays (dfb_info 10 == 3), a single such plane stays on the band
+    matrices (0): plane p of the batch and the single-plane handle with plane_id + p then agree to rounding (<= 1e-13 of the rms,
+    far inside the 1e-12 gate each form passes against the oracle); bit for bit if they happen to run the same form."""
+    if not O.have_ref():
+        pytest.skip("needs the data files under oracle/_ref")
+    P, p = 8, 5
+    batch = dfb.DIGITAL_FILTER(dfb.DFConfig(vel_fluc_file=O.RST_DAT, line_file=O.LINE_DAT, seed=21, plane_id=2), fetch=False, nplanes=P)
+    cfg1 = dfb.DFConfig(vel_fluc_file=O.RST_DAT, line_file=O.LINE_DAT, seed=21, plane_id=2 + p)
+    single = dfb.DIGITAL_FILTER(cfg1, fetch=False)
+    same_form = batch.info(10) == single.info(10)
+    for dt in (1e-5, 1e-5, 2e-5):
+        batch.filter(dt); single.filter(dt)
+    worst = 0.0
+    for w in (dfb.U_FLUC, dfb.V_FLUC, dfb.W_FLUC, dfb.T_FLUC, dfb.RHO_FLUC):
+        a, b = batch.get(w, plane=p), single.get(w)
+        if same_form:
+            assert np.array_equal(a, b), w
+        ok, ratio = normwise_close(a, b, 1e-13)
+        worst = max(worst, ratio)
+        assert ok, (w, ratio)
+    print("config 5 default plane: batch form %d, single form %d, worst normwise difference %.2e" % (batch.info(10), single.info(10), worst))
+    batch.close(); single.close()
+
+
 def test_config5_batch_statistics_per_plane(dfb, W):
     plane = W.plane_profile(40, 96, 8, 6)
     batch = dfb.DIGITAL_FILTER(dfb.DFConfig.from_plane(plane, seed=4), nplanes=3)
