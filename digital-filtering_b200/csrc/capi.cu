@@ -638,10 +638,20 @@ void build_device(dfb_filter_s& H) {
             H.yp[0].r_nbuf = r_nbuf;
             H.yp[0].r_smem = (int)ysweep_run_smem(r_wrows, r_nbuf);
             H.yp[0].r_grid = yprop.multiProcessorCount;
+            {
+                // tile queue of the persistent grid, one per buffer set: {next tile, producers done}; it rests at the grid size
+                // (CTA b starts on tile b) and the kernel puts it back there when its last producer has finished
+                const int grid = (int)std::min<long long>((long long)rt.size() * NP, (long long)H.yp[0].r_grid);
+                const int init[4] = {grid, 0, grid, 0};
+                int* rc = H.dalloc<int>(4, false);             // (no asynchronous zero fill behind the copy below)
+                CUDA_TRY(cudaMemcpy(rc, init, sizeof(init), cudaMemcpyHostToDevice));
+                H.yp[0].rcounter = rc;
+            }
             CUDA_TRY(ysweep_run_prepare((size_t)H.yp[0].r_smem));
         }
         H.yp[1] = H.yp[0];
         H.yp[1].D = H.D[1];
+        if (H.yp[1].rcounter) H.yp[1].rcounter += 2;
         H.n_items = (int)tiles.size();
         for (int b = 0; b < 2; ++b)
         for (int f = 0; f < 3; ++f) {

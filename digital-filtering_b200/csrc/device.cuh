@@ -145,6 +145,7 @@ struct YParams {
     int r_wrows;               // rows of one window buffer (largest window, whole boxes)
     int r_nbuf;                // window buffers: 2, or 1 when two of the plane's tallest windows do not fit
     int r_grid;                // CTAs of the persistent grid (one per SM)
+    int* rcounter;             // [2] tile queue of the run-recursive kernel: next tile (rests at r_grid between launches), CTAs done
     int tile0;                 // first tile of this launch in `tiles` (dense tiles first, then recursive tiles)
     int n_tiles;               // tiles of this launch (dense kernel: walked with stride gridDim.x)
     int tk;                    // columns per dense tile: 128, or 64 for planes that do not fill the GPU (never with recursive tiles)
