@@ -198,6 +198,20 @@ StreamWaitValue64Fn stream_wait_value64() {
 
 void timeline_reset(dfb_filter_s& H);
 
+// Tile queues of the run-recursive y-sweep (one per buffer set: {next tile, producers done}): at rest they hold the size of the
+// persistent grid -- CTA b starts on tile b, the kernel puts the value back when its last producer has finished.  Written here
+// when the plan is built and again whenever the grid changes (dfb_comm_init leaving SMs free for NCCL); the stream is idle then.
+void reset_run_queues(dfb_filter_s& H) {
+    if (!H.yp[0].rcounter) return;
+    CUDA_TRY(cudaStreamSynchronize(H.stream));
+    if (H.side) CUDA_TRY(cudaStreamSynchronize(H.side));
+    for (int b = 0; b < 2; ++b) {
+        const int grid = (int)std::min<long long>((long long)H.yp[b].n_rtiles * H.nplanes, (long long)H.yp[b].r_grid);
+        const int init[2] = {grid, 0};
+        CUDA_TRY(cudaMemcpy(H.yp[b].rcounter, init, sizeof(init), cudaMemcpyHostToDevice));
+    }
+}
+
 void build_device(dfb_filter_s& H) {
     const Plan& P = H.plan;
     PlaneDev& D = H.D[0];
@@ -638,20 +652,13 @@ void build_device(dfb_filter_s& H) {
             H.yp[0].r_nbuf = r_nbuf;
             H.yp[0].r_smem = (int)ysweep_run_smem(r_wrows, r_nbuf);
             H.yp[0].r_grid = yprop.multiProcessorCount;
-            {
-                // tile queue of the persistent grid, one per buffer set: {next tile, producers done}; it rests at the grid size
-                // (CTA b starts on tile b) and the kernel puts it back there when its last producer has finished
-                const int grid = (int)std::min<long long>((long long)rt.size() * NP, (long long)H.yp[0].r_grid);
-                const int init[4] = {grid, 0, grid, 0};
-                int* rc = H.dalloc<int>(4, false);             // (no asynchronous zero fill behind the copy below)
-                CUDA_TRY(cudaMemcpy(rc, init, sizeof(init), cudaMemcpyHostToDevice));
-                H.yp[0].rcounter = rc;
-            }
+            H.yp[0].rcounter = H.dalloc<int>(4, false);          // tile queues, filled by reset_run_queues() below
             CUDA_TRY(ysweep_run_prepare((size_t)H.yp[0].r_smem));
         }
         H.yp[1] = H.yp[0];
         H.yp[1].D = H.D[1];
         if (H.yp[1].rcounter) H.yp[1].rcounter += 2;
+        reset_run_queues(H);
         H.n_items = (int)tiles.size();
         for (int b = 0; b < 2; ++b)
         for (int f = 0; f < 3; ++f) {
@@ -1801,6 +1808,7 @@ int dfb_comm_init(dfb_handle h, const void* id128, int rank, int world) {
                     const int per_sm = std::max(1, h->zp[b].nblocks / prop.multiProcessorCount);
                     if (h->zp[b].nblocks > per_sm * sms) h->zp[b].nblocks = per_sm * sms;
                 }
+            reset_run_queues(*h);
         }
     });
 }
