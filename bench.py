@@ -534,6 +534,7 @@ def run_b200(args, plane):
     zmode = "recursive" if df.info(7) == 1 else "direct"
     y_form = {3: "run-recursive on the row blocks where it pays + dense band matrices on the rest", 2: "run-recursive",
               1: "chunk-recursive band matrices", 0: "dense band matrices"}[int(df.info(10))]
+    launches_per_step = 4 if int(df.info(10)) == 3 else 3     # noise + y-sweep (two launches when both forms serve the plane) + z-sweep/epilogue
     y_bytes = 3 * 16 * cells                                  # y-sweep: r_ys read once, r_zs interior written once, per field
     yname = "ysweep_run_kernel" if df.info(10) >= 2 else "ysweep_tma_kernel"
     kern = {
@@ -639,7 +640,7 @@ def run_b200(args, plane):
     line = dict(metric=METRIC, value=value, unit="cell-updates/s", n_gpus=world, steps=K, warmup=Wm, ms_per_step=step_ms,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
                 config=cfg, workload_detail=extra,
-                clocks=clocks, gpu_launches=3 * K, wall_ms_per_step=1e3 * t_wall / K,
+                clocks=clocks, gpu_launches=launches_per_step * K, wall_ms_per_step=1e3 * t_wall / K,
                 e2e=dict(value=e2e_value, unit="cell-updates/s", h2d_bytes_per_step=8, d2h_bytes_per_step=40 * cells, steps=Ke,
                          call="dfb_filter_to_host (filter(dt) + u',v',w',T',rho' into pinned host arrays); input is the scalar dt",
                          pipelined=dict(value=e2e_pipelined, unit="cell-updates/s",
