@@ -731,7 +731,7 @@ __global__ void __launch_bounds__(32 * (YR_CONSUMERS + 1), 1) ysweep_run_kernel(
                 //   F_{j+1} = a F_j + (x_{j+1} - a^(N+1) x_{j-N}),      B_{j+1} = B_j / a + (a^N x_{j+1+N} - x_j / a),
                 // nothing is kept per row, one dependent FMA per row and sum.  The B walk runs against its stable direction: an error
                 // grows by 1/a per row, so the planner bounds the group length by exp(2 pi R / N) <= 8 (R <= 0.33 N): measured
-                // deviation from the direct sum <= 2.5e-15 of the rms at the bound (gate 1e-12).
+                // deviation from the direct sum <= 6e-15 of the rms at the bound (tests/test_run_form_bound.py; gate 1e-12).
                 const double ia = __drcp_rn(a), aN = __dmul_rn(-naN1, ia);
                 double xc = col[c * YR_C];
                 {
