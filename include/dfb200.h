@@ -112,7 +112,7 @@ int dfb_dims(dfb_handle h, int* Ny, int* Nz);
  * 7 form of the z-sweep in use: 1 = recursive evaluation of the exponential window, 0 = direct Toeplitz sum,
  * 8 / 9 y-sweep tiles of the band-matrix kernels evaluated recursively / with dense band matrices,
  * 10 form of the y-sweep in use: 2 = run-recursive (every row group through the exponential window), 3 = run-recursive on the blocks of
- *    32 rows where it pays + dense band matrices on the rest (e.g. the reference's default plane), 1 = chunk-recursive band-matrix
+ *    32 rows where it pays + dense band matrices on the rest (e.g. a batch of planes of the reference's default geometry), 1 = chunk-recursive band-matrix
  *    kernel, 0 = dense band matrices (DFB_Y_MODE=0|1|2 forces a form), 11 tiles of the run-recursive kernel, 12 transport of the config-4 hand-off: 2 = peer-to-peer copies (CUDA IPC + copy engines), 1 = NCCL
  *    send/recv, 0 = no communicator */
 int dfb_info(dfb_handle h, int what, int field, int64_t* out64);
